@@ -1,0 +1,173 @@
+"""CPU tests: pin oracle/ (the CPU restatement) against the golden vectors generated from
+the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention as oattn
+from oracle import gridsample as ogs
+from oracle import lang as olang
+from oracle import pooling as opool
+from oracle import ptv3 as optv3
+from oracle import serialization as oser
+from oracle import subm_conv as oconv
+
+ORDERS = oser.ORDERS
+
+
+@pytest.mark.parametrize("depth", [1, 2, 5, 9, 10, 16])
+def test_encode_matches_reference(golden, depth):
+    g = golden("serialization.npz")
+    grid, batch, ref = g[f"grid_d{depth}"], g[f"batch_d{depth}"], g[f"code_d{depth}"]
+    for k, o in enumerate(ORDERS):
+        np.testing.assert_array_equal(oser.encode(grid, batch, depth, o), ref[k])
+
+
+@pytest.mark.parametrize("depth", [2, 5, 9, 16])
+def test_code_hierarchy_property(depth):
+    """code >> 3 == code of (coord >> 1) at depth-1 for all four orders (what pooling relies on)."""
+    rng = np.random.default_rng(depth)
+    g = rng.integers(0, 1 << depth, (500, 3))
+    for o in ORDERS:
+        a = oser.encode(g, None, depth, o) >> 3
+        b = oser.encode(g >> 1, None, depth - 1, o)
+        np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_point_serialization_matches_reference(golden, shuffle):
+    g = golden("serialization.npz")
+    tag = "shuf" if shuffle else "noshuf"
+    grid, offset = g["ps_grid"], g["ps_offset"]
+    batch = oser.offset2batch(offset)
+    code, order, inv, depth = oser.serialization(grid, batch, len(offset), ORDERS,
+                                                 perm=g["ps_perm"] if shuffle else None)
+    assert depth == int(g[f"ps_depth_{tag}"])
+    np.testing.assert_array_equal(code, g[f"ps_code_{tag}"])
+    np.testing.assert_array_equal(order, g[f"ps_order_{tag}"])
+    np.testing.assert_array_equal(inv, g[f"ps_inverse_{tag}"])
+
+
+@pytest.mark.parametrize("name", ["room", "boundary"])
+def test_gridsample_matches_reference(golden, name):
+    g = golden("gridsample.npz")
+    coord = g[f"{name}_coord_in"]
+    res = ogs.grid_sample_train(coord, 0.02)
+    np.testing.assert_array_equal(res["inverse"], g[f"{name}_inverse"])
+    np.testing.assert_array_equal(res["grid_coord"], g[f"{name}_grid_coord"])
+    # the representative is RNG/introsort dependent in the reference: check membership
+    ref_out = g[f"{name}_coord_out"]
+    vox_ref, _ = ogs.voxelize(ref_out, 0.02)
+    # min subtraction differs (subset), so compare absolute voxel indices
+    a = np.floor(ref_out.astype(np.float64) / 0.02).astype(np.int64)
+    b = np.floor(coord[res["idx_unique"]].astype(np.float64) / 0.02).astype(np.int64)
+    np.testing.assert_array_equal(a, b)
+    parts, ix = ogs.grid_sample_test(coord, 0.02)
+    assert len(parts) == int(g[f"{name}_n_frag"])
+    np.testing.assert_array_equal([p.shape[0] for p in parts], g[f"{name}_frag_sizes"])
+    # last fragment: same voxel per slot as the reference's
+    np.testing.assert_array_equal(ix["inverse"][parts[-1]], ix["inverse"][g[f"{name}_frag_last_index"]])
+
+
+def test_fnv_hash_is_mul_then_xor():
+    h = ogs.fnv_hash_vec(np.array([[1, 2, 3]]))
+    x = 14695981039346656037
+    for v in (1, 2, 3):
+        x = (x * 1099511628211) % (1 << 64)
+        x ^= v
+    assert int(h[0]) == x
+
+
+def test_patch_table_matches_reference(golden):
+    g = golden("patch_table.npz")
+    for i in range(int(g["n_cases"])):
+        pad, unpad, cu = oattn.patch_table(g[f"c{i}_offset"], int(g[f"c{i}_K"]))
+        np.testing.assert_array_equal(pad, g[f"c{i}_pad"])
+        np.testing.assert_array_equal(unpad, g[f"c{i}_unpad"])
+        np.testing.assert_array_equal(cu, g[f"c{i}_cu"])
+
+
+def test_pooling_matches_reference(golden):
+    g = golden("pooling.npz")
+    offset = g["offset"]
+    batch = oser.offset2batch(offset)
+    code, order, inv, depth = oser.serialization(g["grid_coord"], batch, len(offset), ORDERS, perm=g["perms"][0])
+    np.testing.assert_array_equal(code, g["parent_code"])
+    ix = opool.pool_index(code, 1, perm=g["perms"][1])
+    np.testing.assert_array_equal(ix["cluster"], g["cluster"])
+    np.testing.assert_array_equal(ix["code"], g["code"])
+    np.testing.assert_array_equal(ix["order"], g["order"])
+    np.testing.assert_array_equal(ix["inverse"], g["inverse"])
+    gc, b = opool.pooled_attrs(g["grid_coord"], batch, ix["head"], 1)
+    np.testing.assert_array_equal(gc, g["out_grid_coord"])
+    np.testing.assert_array_equal(b, g["out_batch"])
+    assert depth - 1 == int(g["depth"])
+    coord = opool.segment_csr(g["coord"], ix["indices"], ix["idx_ptr"], "mean")
+    np.testing.assert_allclose(coord, g["out_coord"], rtol=1e-6, atol=1e-6)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    proj = torch.nn.functional.linear(torch.from_numpy(g["feat"]), sd["proj.weight"], sd["proj.bias"])
+    feat = torch.from_numpy(opool.segment_csr(proj.numpy(), ix["indices"], ix["idx_ptr"], "mean"))
+    feat = torch.nn.functional.gelu(torch.nn.functional.batch_norm(
+        feat, sd["norm.0.running_mean"], sd["norm.0.running_var"], sd["norm.0.weight"], sd["norm.0.bias"],
+        training=False, eps=1e-3))
+    np.testing.assert_allclose(feat.numpy(), g["out_feat"], rtol=1e-5, atol=1e-5)
+
+
+def test_losses_match_reference(golden):
+    g = golden("losses.npz")
+    pred = torch.from_numpy(g["pred"].astype(np.float32))
+    target = torch.from_numpy(g["target"].astype(np.float32))
+    mask = torch.from_numpy(g["mask"])
+    seg = torch.from_numpy(g["segment"])
+    half = torch.from_numpy(g["half"])
+    np.testing.assert_allclose(olang.cosine_loss(pred, target, mask).numpy(), g["cos"], rtol=1e-6)
+    np.testing.assert_allclose(olang.l2_loss(pred, target, mask).numpy(), g["l2"], rtol=1e-6)
+    labs, A, B = olang.class_half_sums(pred, mask, seg, half)
+    assert labs.tolist() == [0, 1, 2, 5]
+    con = olang.contrastive_from_sums(A, B, 0.2, 0.025)
+    np.testing.assert_allclose(con.numpy(), g["con"], rtol=1e-5)
+    probs, mx, label = olang.zero_shot_head(pred, torch.from_numpy(g["text"]))
+    np.testing.assert_allclose(mx.numpy(), g["max_prob"], rtol=1e-6)
+    np.testing.assert_array_equal(label.numpy(), g["argmax"])
+
+
+def test_subm_conv_against_dense_conv3d():
+    rng = np.random.default_rng(0)
+    g = np.unique(rng.integers(0, 12, (400, 3)), axis=0)
+    torch.manual_seed(0)
+    for k, cin, cout, bias in ((3, 8, 6, True), (5, 11, 4, False)):
+        feat = torch.randn(g.shape[0], cin)
+        w = torch.randn(cout, k, k, k, cin) * 0.1
+        b = torch.randn(cout) if bias else None
+        nbr = oconv.kernel_map(g, np.zeros(g.shape[0], dtype=np.int64), k)
+        out = oconv.subm_conv(feat, nbr, w, b)
+        ref = oconv.dense_conv3d_check(feat, g, w, b)
+        np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+        # centre tap is the identity map; taps are symmetric: nbr[nbr[p,t], k^3-1-t] == p
+        c = (k ** 3) // 2
+        np.testing.assert_array_equal(nbr[:, c], np.arange(g.shape[0]))
+        t = 0
+        rows = np.nonzero(nbr[:, t] >= 0)[0]
+        np.testing.assert_array_equal(nbr[nbr[rows, t], k ** 3 - 1 - t], rows)
+
+
+def test_kernel_map_respects_batch():
+    g = np.array([[0, 0, 0], [1, 0, 0], [1, 0, 0]])
+    b = np.array([0, 0, 1])
+    nbr = oconv.kernel_map(g, b, 3)
+    # voxel 2 (batch 1) has no neighbours besides itself
+    assert (nbr[2] >= 0).sum() == 1 and nbr[2, 13] == 2
+    assert (nbr[0] >= 0).sum() == 2
+
+
+def test_ptv3_small_matches_reference(golden):
+    from tests.golden.make_golden import SMALL_CFG
+    g = golden("ptv3_small.npz")
+    sd = {k[3:]: torch.from_numpy(g[k].astype(np.float32) if g[k].dtype == np.float16 else g[k])
+          for k in g.files if k.startswith("sd.")}
+    taps = {}
+    out = optv3.ptv3_forward(sd, SMALL_CFG, g["coord"], g["grid_coord"], g["feat"], g["offset"],
+                             perms=list(g["perms"]), taps=taps)
+    ref = g["out_feat"]
+    err = np.abs(out.numpy() - ref).max()
+    assert err < 2e-4 * max(1.0, np.abs(ref).max()), err
