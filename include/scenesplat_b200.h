@@ -1,0 +1,196 @@
+/* scenesplat_b200 -- C-ABI of the B200 (sm_100a) kernels behind SceneSplat's PTv3 3DGS encoder hot path.
+ *
+ * The reference (zenghjian/SceneSplat) has no C/FFI plugin interface for this path: its boundary is
+ * Python (registries + the `Point` dict) over three third-party operator
+ * libraries (spconv, torch_scatter, flash_attn) and ATen built-ins.  The native convention of the
+ * reference's OWN extensions is free functions taking raw device pointers + ints, caller-allocated
+ * outputs (libs/pointops/src/pointops_api.cpp:15-32, libs/pointops/functions/query.py:7-25).  This
+ * header follows that convention without torch types in the signatures:
+ *
+ *   - every pointer is DEVICE memory owned by the caller (torch's caching allocator in practice),
+ *     unless a parameter name ends in `_host`;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), never allocates,
+ *     and takes scratch from a caller-provided workspace sized by the matching *_workspace_bytes();
+ *   - return value: 0 = ok, -1 = bad arguments, otherwise a cudaError_t;
+ *   - no global state: thread-safe per stream.
+ *
+ * dtype flags: *_is_bf16 = 1 -> __nv_bfloat16 elements, 0 -> float.
+ * order ids: 0 = "z", 1 = "z-trans", 2 = "hilbert", 3 = "hilbert-trans".
+ */
+#ifndef SCENESPLAT_B200_H_
+#define SCENESPLAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Serialization.  Replaces Point.serialization (pointcept/models/utils/structure.py:47-102):
+ * encode x4 (serialization/default.py:8-24) + torch.argsort + scatter_ inverse, and offset2batch
+ * (pointcept/models/utils/misc.py:19-24). */
+
+/* max over all grid coordinates -> *out_max_dev (structure.py:66: depth = bit_length(max)). */
+int ss_coord_max(const void* grid_coord, int coord_is_int32, int64_t n, int64_t* out_max_dev, void* stream);
+
+size_t ss_serialize_workspace_bytes(int64_t n, int rows, int depth, int n_batch);
+
+/* grid_coord [n,3] int64 (or int32), offset [n_batch] cumulative counts.  rows <= 4 output rows,
+ * row r encoded with order_ids_host[r] (the shuffle_orders permutation is applied by the caller by
+ * permuting the ids).  Outputs: batch_out [n] (nullable), code/order/inverse [rows, n] int64.
+ * Ties (duplicate voxels inside one batch item) are ordered by original index (stable). */
+int ss_serialize(const void* grid_coord, int coord_is_int32, const int64_t* offset, int n_batch, int64_t n, int depth,
+                 int rows, const int* order_ids_host, int64_t* batch_out, int64_t* code, int64_t* order,
+                 int64_t* inverse, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GridSample.  Replaces GridSample.__call__ (pointcept/datasets/transform.py:1211-1330) and
+ * fnv_hash_vec / ravel_hash_vec (:1384-1416).  hash_type: 0 = fnv, 1 = ravel. */
+size_t ss_gridsample_workspace_bytes(int64_t n);
+
+/* coord [n,3] f32.  Outputs: idx_sort [n] (points sorted by voxel hash, stable), inverse [n] (voxel rank
+ * of every raw point), start [n+1] (first sorted position of every voxel, start[M] = n), *m_dev = M,
+ * min_coord_dev [3] (voxel-index minimum that was subtracted). */
+int ss_gridsample_index(const float* coord, int64_t n, double grid_size, int hash_type, int64_t* idx_sort,
+                        int64_t* inverse, int64_t* start, int64_t* m_dev, int64_t* min_coord_dev, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Representative of every voxel: member (rnd[v] % count[v]) when rnd != NULL (train mode,
+ * transform.py:1264-1268) else member (frag % count[v]) (test-mode fragment `frag`, :1304-1306).
+ * Outputs sized for the upper bound n: idx_unique [M], grid_coord_out [M,3] (nullable), count_out [M] (nullable). */
+int ss_gridsample_select(const float* coord, int64_t n, double grid_size, const int64_t* min_coord_dev,
+                         const int64_t* idx_sort, const int64_t* start, const int64_t* m_dev, const int64_t* rnd,
+                         int64_t frag, int64_t* idx_unique, int64_t* grid_coord_out, int64_t* count_out, void* stream);
+
+/* dst[v,:] = src[idx[v],:], rows of row_bytes; row count = *count_dev when non-NULL else count. */
+int ss_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, const int64_t* count_dev, int64_t count,
+                   void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SerializedPooling / SerializedUnpooling (point_transformer_v3m1_base.py:371-444, 471-482). */
+size_t ss_pool_workspace_bytes(int64_t n);
+
+/* Parent code/order [k,n].  Clusters = runs of (code[0] >> 3*pooling_depth) along order[0].
+ * Child row r' is derived from parent row src_row_host[r'] (the child's shuffle permutation).
+ * Child arrays have row stride m_cap (>= n).  Outputs: cluster [n] (= pooling_inverse),
+ * seg_start [n+1] (CSR pointer into order[0]), head [m_cap] (one member per cluster), *m_dev = M,
+ * child code/order/inverse [k,m_cap], child grid_coord [m_cap,3] and batch [m_cap] (nullable, need the
+ * parent's grid_coord / batch). */
+int ss_pool_index(const int64_t* code, const int64_t* order, const int64_t* grid_coord, const int64_t* batch, int64_t n,
+                  int k, int pooling_depth, const int* src_row_host, int64_t m_cap, int64_t* cluster, int64_t* seg_start,
+                  int64_t* head, int64_t* m_dev, int64_t* child_code, int64_t* child_order, int64_t* child_inverse,
+                  int64_t* child_grid_coord, int64_t* child_batch, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* torch_scatter.segment_csr(src[order], seg_start, reduce) (+ optional folded-BN affine and GELU).
+ * reduce: 0 sum, 1 mean, 2 max, 3 min.  act: 0 none, 1 GELU(erf).  Row count = *m_dev if non-NULL else m. */
+int ss_segment_reduce(const void* src, int src_is_bf16, const int64_t* order, const int64_t* seg_start,
+                      const int64_t* m_dev, int64_t m, int channels, int reduce, const float* scale, const float* shift,
+                      int act, void* out, int out_is_bf16, void* stream);
+
+/* out[i,:] = f_a(a[i,:]) + f_b(b[cluster[i],:]); f = optional affine + activation.  out_a (nullable)
+ * receives f_a(a) alone (what the reference's stale sparse_conv_feat holds after unpooling). */
+int ss_unpool_gather_add(const void* a, const void* b, int in_is_bf16, const int64_t* cluster, int64_t n, int channels,
+                         const float* scale_a, const float* shift_a, const float* scale_b, const float* shift_b, int act,
+                         void* out, void* out_a, int out_is_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Submanifold convolution (replaces spconv.SubMConv3d, call sites
+ * point_transformer_v3m1_base.py:277-284 and :499-506). */
+size_t ss_kmap_workspace_bytes(int64_t n, int k);
+
+/* Neighbour table nbr [k^3, n] int32 (tap-major, -1 = inactive) from one sorted serialization row
+ * (code_row/order_row [n], encoded with order_id at `depth`).  tap t = (i*k+j)*k+l <-> (i-r, j-r, l-r).
+ * tap_count_dev [k^3] int64 receives the number of active pairs per tap. */
+int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* batch, const int64_t* code_row,
+                  const int64_t* order_row, int64_t n, int depth, int order_id, int k, int32_t* nbr,
+                  int64_t* tap_count_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Compacted pair lists for the gather-GEMM path: tap t owns rows [tap_base[t], tap_base[t] + count[t])
+ * of the product buffer; pair_in [p_pad] = input row of every product row, ypos [k^3, n] = product row
+ * of (tap, output voxel) or -1. */
+int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k, const int64_t* tap_base_dev,
+                  int64_t p_pad, int32_t* pair_in, int32_t* ypos, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SIMT fp32-accumulate conv: out[p,co] = bias[co] + sum_t sum_ci wt[t][ci][co] * in[nbr[t][p]][ci],
+ * then optional affine (folded BN) + activation.  wt is the [k^3, cin, cout] fp32 re-layout of the
+ * reference weight [cout, k, k, k, cin]. */
+int ss_subm_conv_simt(const void* in, int in_is_bf16, const int32_t* nbr, const float* wt, const float* bias,
+                      const float* scale, const float* shift, int act, int64_t n, int k3, int cin, int cout, void* out,
+                      int out_is_bf16, void* stream);
+
+/* tcgen05 gather-GEMM: prod[r, :] = in[pair_in[r], :] @ w[tap(r)]^T for r < p_pad (bf16 in, fp32
+ * accumulate in TMEM, bf16 out).  w is [k^3, cout, cin] bf16 (K-major), tile_tap_host [p_pad/128]
+ * int32 gives the tap of every 128-row tile.  cin, cout multiples of 16 (cout <= 768...). */
+int ss_subm_conv_gemm(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
+                      int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream);
+
+/* out[p,:] = bias + sum_t prod[ypos[t][p], :]  (fp32 accumulate) -> bf16/fp32 */
+int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float* bias, int64_t n, int k3, int cout,
+                        void* out, int out_is_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SerializedAttention (point_transformer_v3m1_base.py:114-222). */
+
+/* Patch table [max_patches] of int32x4 (q_begin, q_end, kv_begin, kv_end) in sorted positions, built
+ * on the device from offset (no host sync); unused entries are zero.  max_patches >= n/K + n_batch. */
+int ss_patch_table(const int64_t* offset, int n_batch, int patch_size, int max_patches, int32_t* table,
+                   int32_t* n_patches_dev, void* stream);
+
+/* qkv [n, 3*H*d] laid out (3, H, d) per row; order_row [n] = serialized_order[order_index].
+ * out[order_row[j], h*d:(h+1)*d] = softmax(q_j K^T * scale) V over the patch of sorted position j. */
+int ss_patch_attention_simt(const void* qkv, int in_is_bf16, const int64_t* order_row, const int32_t* table,
+                            int max_patches, int patch_size, int heads, int head_dim, float scale, void* out,
+                            int out_is_bf16, void* stream);
+
+/* tcgen05 / TMEM kernel: bf16 in/out, head_dim in {16, 32, 48, 64}, patch_size multiple of 128 (<= 1024). */
+int ss_patch_attention(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
+                       int patch_size, int heads, int head_dim, float scale, void* out_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise fusions around the GEMMs of a Block (point_transformer_v3m1_base.py:318-338). */
+
+/* y = res + f(delta), f = LayerNorm(g0,b0) if g0 else identity; res_out = y (fp32, may alias res);
+ * norm_out = LayerNorm(y; g1,b1) if g1 else cast(y).  Any of res / res_out / norm_out may be NULL. */
+int ss_add_layernorm(const float* res, const void* delta, int delta_is_bf16, const float* g0, const float* b0,
+                     const float* g1, const float* b1, float eps, int64_t n, int channels, float* res_out,
+                     void* norm_out, int norm_is_bf16, void* stream);
+
+/* out = act(x * scale[c] + shift[c]) (scale/shift nullable).  act: 0 none, 1 GELU(erf). */
+int ss_affine_act(const void* x, int in_is_bf16, const float* scale, const float* shift, int act, int64_t n,
+                  int channels, void* out, int out_is_bf16, void* stream);
+
+/* F.normalize(x, p=2, dim=1, eps)  (pointcept/models/default.py:98) */
+int ss_l2_normalize(const void* x, int in_is_bf16, int64_t n, int channels, float eps, void* out, int out_is_bf16,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Language head and losses. */
+
+/* logits = feat @ text^T; probs = sigmoid.  mode 0: max_prob [n], label [n] (-1 if max < threshold)
+ * (pointcept/engines/hooks/evaluator.py:793-800); mode 1: probs_accum[idx[p] or p, :] += probs
+ * (pointcept/engines/test.py:335-349).  normalize != 0 applies F.normalize to the row first. */
+int ss_lang_head(const void* feat, int feat_is_bf16, const float* text, int64_t n, int channels, int n_classes,
+                 int normalize, float threshold, int mode, const int64_t* idx, float* max_prob, int64_t* label,
+                 float* probs_accum, void* stream);
+
+/* acc3 = {sum_valid (1 - cos), sum_valid ||pred - target||^2, n_valid} as doubles
+ * (pointcept/models/losses/misc.py:247-295).  target_dtype: 0 fp32, 1 bf16, 2 fp16. */
+int ss_cos_l2_loss(const void* pred, int pred_is_bf16, const void* target, int target_dtype, const uint8_t* mask,
+                   int64_t n, int channels, double* acc3, void* stream);
+
+/* sums [(label*2 + half), channels] (fp32) and counts [n_classes*2] over valid points
+ * (pointcept/models/losses/misc.py:355-389). */
+int ss_class_half_sums(const void* pred, int pred_is_bf16, const uint8_t* mask, const int64_t* segment,
+                       const int64_t* half, int64_t n, int channels, int n_classes, float* sums, int32_t* counts,
+                       void* stream);
+
+/* Library / build identification. */
+const char* ss_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCENESPLAT_B200_H_ */

@@ -1,0 +1,107 @@
+"""ctypes binding of the C-ABI library ``_C/libscenesplat_b200.so`` (include/scenesplat_b200.h).
+
+There is deliberately NO fallback: if the library cannot be loaded, or a call is made without a CUDA
+device, the product path raises.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libscenesplat_b200.so")
+
+_vp, _i, _i64, _sz, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
+
+# name -> (restype, argtypes); mirrors include/scenesplat_b200.h one to one
+SIGNATURES = {
+    "ss_coord_max": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "ss_serialize_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
+    "ss_serialize": (_i, [_vp, _i, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ss_gridsample_workspace_bytes": (_sz, [_i64]),
+    "ss_gridsample_index": (_i, [_vp, _i64, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ss_gridsample_select": (_i, [_vp, _i64, _d, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ss_gather_rows": (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "ss_pool_workspace_bytes": (_sz, [_i64]),
+    "ss_pool_index": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                           _vp, _sz, _vp]),
+    "ss_segment_reduce": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    "ss_unpool_gather_add": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "ss_kmap_workspace_bytes": (_sz, [_i64, _i]),
+    "ss_kmap_build": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ss_kmap_pairs": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "ss_subm_conv_simt": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _i, _vp]),
+    "ss_subm_conv_gemm": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
+    "ss_subm_conv_reduce": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp]),
+    "ss_patch_table": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "ss_patch_attention_simt": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp]),
+    "ss_patch_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "ss_add_layernorm": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _i64, _i, _vp, _vp, _i, _vp]),
+    "ss_affine_act": (_i, [_vp, _i, _vp, _vp, _i, _i64, _i, _vp, _i, _vp]),
+    "ss_l2_normalize": (_i, [_vp, _i, _i64, _i, _f, _vp, _i, _vp]),
+    "ss_lang_head": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ss_cos_l2_loss": (_i, [_vp, _i, _vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "ss_class_half_sums": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "ss_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc exists).  Raises on failure -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class CudaKernelError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        if rc == -1:
+            raise CudaKernelError(f"{what}: bad arguments")
+        raise CudaKernelError(f"{what}: CUDA error {rc}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None -> NULL).  Tensors must be contiguous CUDA tensors."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CudaKernelError("scenesplat_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise CudaKernelError("scenesplat_b200 kernels need contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def int_array(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def call(name: str, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    check(rc, name)
+
+
+def workspace(nbytes: int, device):
+    return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)

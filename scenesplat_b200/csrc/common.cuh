@@ -1,0 +1,180 @@
+// Shared device helpers for the scenesplat_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define SS_OK 0
+#define SS_BAD_ARGS (-1)
+
+#define SS_CHECK_LAUNCH()                         \
+  do {                                            \
+    cudaError_t e__ = cudaGetLastError();         \
+    if (e__ != cudaSuccess) return (int)e__;      \
+  } while (0)
+
+#define SS_CUDA(x)                                \
+  do {                                            \
+    cudaError_t e__ = (x);                        \
+    if (e__ != cudaSuccess) return (int)e__;      \
+  } while (0)
+
+namespace ss {
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp / block scans (sum), 32-bit.
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane_id() >= (unsigned)o) v += t;
+  }
+  return v;
+}
+
+// Exclusive block scan over blockDim.x (multiple of 32, <= 1024) threads. `smem` needs 33 words.
+// Returns the exclusive prefix of `v`; `total` receives the block sum.  Contains __syncthreads.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem, uint32_t& total) {
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  uint32_t inc = warp_inclusive_scan(v);
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < nwarp ? smem[lane] : 0u;
+    uint32_t winc = warp_inclusive_scan(w);
+    smem[lane] = winc - w;
+    if (lane == 31) smem[32] = winc;
+  }
+  __syncthreads();
+  uint32_t res = smem[warp] + inc - v;
+  total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoupled look-back over tiles for one 32-bit value per (tile, slot).
+// status word: bit31 = inclusive prefix available, bit30 = tile aggregate available, low 30 bits value.
+constexpr uint32_t kFlagInclusive = 0x80000000u;
+constexpr uint32_t kFlagAggregate = 0x40000000u;
+constexpr uint32_t kValueMask = 0x3fffffffu;
+
+// Publishes this tile's aggregate, walks back over earlier tiles and returns the exclusive prefix
+// of all earlier tiles; then publishes the inclusive prefix.  `status` points at slot 0 of tile 0,
+// `stride` = words between consecutive tiles for the same slot.
+__device__ __forceinline__ uint32_t lookback_exclusive(uint32_t* status, int stride, int tile, uint32_t aggregate) {
+  uint32_t* mine = status + (size_t)tile * stride;
+  if (tile == 0) {
+    st_volatile_u32(mine, kFlagInclusive | aggregate);
+    return 0u;
+  }
+  st_volatile_u32(mine, kFlagAggregate | aggregate);
+  uint32_t excl = 0u;
+  for (int t = tile - 1; t >= 0; --t) {
+    const uint32_t* p = status + (size_t)t * stride;
+    uint32_t v;
+    do {
+      v = ld_volatile_u32(p);
+    } while ((v & (kFlagInclusive | kFlagAggregate)) == 0u);
+    excl += v & kValueMask;
+    if (v & kFlagInclusive) break;
+  }
+  st_volatile_u32(mine, kFlagInclusive | (excl + aggregate));
+  return excl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Space-filling-curve codes (bit-exact restatement targets: oracle/serialization.py).
+__device__ __forceinline__ uint64_t spread3(uint64_t x) {  // 16 low bits -> every third bit
+  x &= 0xffffull;
+  x = (x | (x << 32)) & 0x001f00000000ffffull;
+  x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+  x = (x | (x << 8)) & 0x100f00f00f00f00full;
+  x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
+}
+
+// bit i of x -> 3i+2, y -> 3i+1, z -> 3i  (reference z_order.py:42-49)
+__device__ __forceinline__ uint64_t z_key(uint32_t x, uint32_t y, uint32_t z, int depth) {
+  const uint32_t m = (1u << depth) - 1u;
+  return (spread3(x & m) << 2) | (spread3(y & m) << 1) | spread3(z & m);
+}
+
+// Skilling transpose + interleave + Gray decode (reference hilbert.py:156-181)
+__device__ __forceinline__ uint64_t hilbert_key(uint32_t x, uint32_t y, uint32_t z, int depth) {
+  const uint32_t m = (1u << depth) - 1u;
+  uint32_t X0 = x & m, X1 = y & m, X2 = z & m;
+  for (uint32_t Q = 1u << (depth - 1); Q >= 1u; Q >>= 1) {
+    const uint32_t P = Q - 1u;
+    // dim 0
+    if (X0 & Q) X0 ^= P;
+    // dim 1
+    if (X1 & Q) {
+      X0 ^= P;
+    } else {
+      uint32_t t = (X0 ^ X1) & P;
+      X0 ^= t;
+      X1 ^= t;
+    }
+    // dim 2
+    if (X2 & Q) {
+      X0 ^= P;
+    } else {
+      uint32_t t = (X0 ^ X2) & P;
+      X0 ^= t;
+      X2 ^= t;
+    }
+  }
+  uint64_t h = (spread3(X0) << 2) | (spread3(X1) << 1) | spread3(X2);
+  h ^= h >> 1;
+  h ^= h >> 2;
+  h ^= h >> 4;
+  h ^= h >> 8;
+  h ^= h >> 16;
+  h ^= h >> 32;
+  return h;
+}
+
+// order ids: 0 = z, 1 = z-trans, 2 = hilbert, 3 = hilbert-trans (reference serialization/default.py:8-24)
+__device__ __forceinline__ uint64_t sfc_key(int order_id, uint32_t x, uint32_t y, uint32_t z, int depth) {
+  switch (order_id) {
+    case 0: return z_key(x, y, z, depth);
+    case 1: return z_key(y, x, z, depth);
+    case 2: return hilbert_key(x, y, z, depth);
+    default: return hilbert_key(y, x, z, depth);
+  }
+}
+
+}  // namespace ss

@@ -1,0 +1,248 @@
+// Submanifold convolution on the 5th-gen tensor cores: gather-GEMM over compacted (input, output)
+// pairs grouped by tap, fp32 accumulation in TMEM, then a gather-sum over taps.
+//
+// Replaces (reference): spconv.SubMConv3d forward for the xCPE 3^3 convs
+// (point_transformer_v3m1_base.py:277-284; fp32 in the reference, bf16 x bf16 -> fp32 here).
+//
+// Stage 1 (gather_gemm_kernel): product row r (tap t = tile_tap[r/128]) = X[pair_in[r], :] @ W_t^T.
+//   CTA = 128 product rows x BN output channels.  Warps 0-3 gather the A rows with 16-byte cp.async
+//   into a 128B-swizzled K-major tile (8 lanes cover one 128-byte row segment -> full-line requests),
+//   warp 4 streams the W_t tile with TMA, warp 5 issues tcgen05.mma (M=128, N=BN, K=16) into TMEM;
+//   warps 0-3 then drain TMEM (tcgen05.ld) to bf16.  Only ACTIVE pairs are multiplied: FLOPs =
+//   2 * pairs * Cin * Cout (an output-stationary dense-tap kernel would do 27/7.2 = 3.75x more on
+//   surface data).  2 CTAs are co-resident per SM so one CTA's epilogue overlaps the other's main loop.
+// Stage 2 (conv_reduce_kernel): out[p, :] = bias + sum_t prod[ypos[t][p], :]  (HBM-bound gather-sum).
+#include "tc_common.cuh"
+#include "../../include/scenesplat_b200.h"
+
+namespace ss {
+
+constexpr int kGemmThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kBK = 64;  // bf16 elements per K chunk = one 128-byte swizzle row
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = kTileM * kBK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 1024 /*barriers, indices*/ + 1024 /*alignment slack*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads)
+gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restrict__ pair_in,
+                   const __grid_constant__ CUtensorMap tmap_w, const int32_t* __restrict__ tile_tap, int cin, int cout,
+                   __nv_bfloat16* __restrict__ prod) {
+  using S = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+  int32_t* s_rows = (int32_t*)(smem + S::kBarOffset + 256);  // [128] gathered input rows
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int n0 = blockIdx.y * BN;
+  const int tap = tile_tap[tile];
+  const int nk = (cin + kBK - 1) / kBK;
+
+  if (threadIdx.x < kTileM) s_rows[threadIdx.x] = pair_in[(size_t)tile * kTileM + threadIdx.x];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(&full_bar[s], 128 + 1);  // 128 cp.async producers + 1 TMA expect_tx arrive
+      tc::mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
+    }
+    tc::mbar_init(accum_bar, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap_w);
+  if (warp == 5) tc::tmem_alloc<BN>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ A producers (gather)
+    const int tid = threadIdx.x;  // 0..127
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % STAGES, it = kc / STAGES;
+      tc::mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+      const uint32_t a_base = tc::smem_u32(smem + s * S::kStageBytes);
+      const int k0 = kc * kBK;
+      const int kchunks = min(kBK, cin - k0) >> 3;  // valid 16-byte chunks in this K chunk
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int q = i * 128 + tid;
+        const int r = q >> 3, c = q & 7;
+        if (c < kchunks) {
+          const __nv_bfloat16* src = X + (size_t)s_rows[r] * cin + k0 + c * 8;
+          tc::cp_async16(a_base + tc::sw128_offset(r, c), src);
+        }
+      }
+      tc::cp_async_mbar_arrive_noinc(&full_bar[s]);
+    }
+    // ------------------------------------------------------------------ epilogue: TMEM -> bf16 -> global
+    tc::mbar_wait(accum_bar, 0);
+    tc::tc_fence_after();
+    const int row = warp * 32 + lane;
+    __nv_bfloat16* orow = prod + ((size_t)tile * kTileM + row) * cout + n0;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      if (n0 + j * 32 >= cout) break;
+      uint32_t v[32];
+      tc::tmem_ld32(t_lane + j * 32, v);
+      tc::tmem_ld_wait();
+      uint4* dst = reinterpret_cast<uint4*>(orow + j * 32);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 o;
+        o.x = tc::pack_bf16(__uint_as_float(v[u * 8 + 0]), __uint_as_float(v[u * 8 + 1]));
+        o.y = tc::pack_bf16(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3]));
+        o.z = tc::pack_bf16(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5]));
+        o.w = tc::pack_bf16(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7]));
+        dst[u] = o;
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ B producer (TMA, one lane)
+    if (lane == 0) {
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % STAGES, it = kc / STAGES;
+        tc::mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&full_bar[s], S::kBBytes);
+        tc::tma_load_2d(tc::smem_u32(smem + s * S::kStageBytes + S::kABytes), &tmap_w, kc * kBK, tap * cout + n0,
+                        &full_bar[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(kTileM, BN);
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % STAGES, it = kc / STAGES;
+        tc::mbar_wait(&full_bar[s], it & 1);
+        tc::tc_fence_after();
+        const uint32_t a_addr = tc::smem_u32(smem + s * S::kStageBytes);
+        const uint32_t b_addr = a_addr + S::kABytes;
+        const int ksteps = min(kBK, cin - kc * kBK) >> 4;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t da = tc::umma_desc_sw128(a_addr + k * 32);
+          const uint64_t db = tc::umma_desc_sw128(b_addr + k * 32);
+          tc::umma_bf16(tmem_base, da, db, idesc, (kc | k) ? 1u : 0u);
+        }
+        tc::umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
+      }
+      tc::umma_commit(accum_bar);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// out[p, :] = bias + sum_t prod[ypos[t][p], :]; one warp per output voxel, 16-byte (8 x bf16) lanes.
+template <typename TO>
+__global__ void __launch_bounds__(256)
+conv_reduce_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __restrict__ ypos,
+                   const float* __restrict__ bias, int64_t n, int k3, int cout, TO* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp0; p < n; p += nwarp) {
+    for (int c0 = lane * 8; c0 < cout; c0 += 256) {
+      float acc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = bias ? bias[c0 + u] : 0.f;
+      for (int t = 0; t < k3; ++t) {
+        const int32_t pos = ypos[(size_t)t * n + p];
+        if (pos < 0) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(prod + (size_t)pos * cout + c0);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __bfloat1622float2(h[u]);
+          acc[2 * u] += f.x;
+          acc[2 * u + 1] += f.y;
+        }
+      }
+      if constexpr (sizeof(TO) == 2) {
+        uint4 o;
+        o.x = tc::pack_bf16(acc[0], acc[1]);
+        o.y = tc::pack_bf16(acc[2], acc[3]);
+        o.z = tc::pack_bf16(acc[4], acc[5]);
+        o.w = tc::pack_bf16(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(out + (size_t)p * cout + c0) = o;
+      } else {
+        float4* o = reinterpret_cast<float4*>(out + (size_t)p * cout + c0);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_gather_gemm(const void* X, const int32_t* pair_in, const CUtensorMap& tmap, const int32_t* tile_tap,
+                              int64_t tiles, int cin, int cout, void* prod, cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES>;
+  auto kern = gather_gemm_kernel<BN, STAGES>;
+  SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  dim3 grid((unsigned)tiles, (unsigned)((cout + BN - 1) / BN));
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>((const __nv_bfloat16*)X, pair_in, tmap, tile_tap, cin, cout,
+                                                  (__nv_bfloat16*)prod);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+}  // namespace ss
+
+extern "C" {
+
+int ss_subm_conv_gemm(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
+                      int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (k3 < 1 || p_pad < 0 || p_pad % ss::kTileM != 0 || cin < 16 || cin % 16 != 0 || cout < 32 || cout % 32 != 0) return SS_BAD_ARGS;
+  if (p_pad == 0) return SS_OK;
+  if (!in_bf16 || !pair_in || !w_bf16 || !tile_tap || !prod_bf16) return SS_BAD_ARGS;
+  if (((uintptr_t)in_bf16 | (uintptr_t)w_bf16 | (uintptr_t)prod_bf16) % 16 != 0) return SS_BAD_ARGS;
+  const int64_t tiles = p_pad / ss::kTileM;
+  const int bn = cout >= 256 ? 256 : (cout > 64 ? 128 : (cout > 32 ? 64 : 32));
+  // W viewed as one [k3 * cout, cin] K-major matrix; rows past the last tap read as zero (TMA OOB fill)
+  CUtensorMap tmap;
+  int rc = ss::make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)k3 * cout, (uint64_t)cin, (uint32_t)bn, ss::kBK);
+  if (rc) return rc;
+  switch (bn) {
+    case 256: return ss::launch_gather_gemm<256, 2>(in_bf16, pair_in, tmap, tile_tap, tiles, cin, cout, prod_bf16, stream);
+    case 128: return ss::launch_gather_gemm<128, 3>(in_bf16, pair_in, tmap, tile_tap, tiles, cin, cout, prod_bf16, stream);
+    case 64: return ss::launch_gather_gemm<64, 4>(in_bf16, pair_in, tmap, tile_tap, tiles, cin, cout, prod_bf16, stream);
+    default: return ss::launch_gather_gemm<32, 4>(in_bf16, pair_in, tmap, tile_tap, tiles, cin, cout, prod_bf16, stream);
+  }
+}
+
+int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float* bias, int64_t n, int k3, int cout,
+                        void* out, int out_is_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || k3 < 1 || cout < 8 || cout % 8 != 0) return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if (!prod_bf16 || !ypos || !out) return SS_BAD_ARGS;
+  const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8), 32 * ss::kNumSMs);
+  if (out_is_bf16)
+    ss::conv_reduce_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)prod_bf16, ypos, bias, n, k3,
+                                                                      cout, (__nv_bfloat16*)out);
+  else
+    ss::conv_reduce_kernel<float><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)prod_bf16, ypos, bias, n, k3, cout,
+                                                              (float*)out);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+}  // extern "C"

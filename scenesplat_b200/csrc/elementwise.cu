@@ -1,0 +1,251 @@
+// Fused row-wise kernels around the GEMMs of a PTv3 Block (reference
+// point_transformer_v3m1_base.py:318-338): residual add + (inner) LayerNorm + (outer) LayerNorm in
+// one pass over the row, eval-mode BatchNorm folded to scale/shift + GELU, exact-erf GELU, and
+// F.normalize (pointcept/models/default.py:98).  One warp per row; the row lives in registers.
+#include "common.cuh"
+#include "../../include/scenesplat_b200.h"
+
+namespace ss {
+
+template <typename T> __device__ __forceinline__ float e_in(T v);
+template <> __device__ __forceinline__ float e_in<float>(float v) { return v; }
+template <> __device__ __forceinline__ float e_in<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T e_out(float v);
+template <> __device__ __forceinline__ float e_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 e_out<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+__device__ __forceinline__ float e_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kMaxPerLane = 32;  // C <= 1024
+
+// y = res + f(delta),  f = LayerNorm(g0, b0) when g0 != null else identity;  res may be null (y = f(delta)).
+// Writes res_out (fp32, may alias res) and/or norm_out = LayerNorm(y; g1, b1) (or a plain cast of y when g1 == null).
+template <typename TD, typename TN, int VPL>
+__global__ void __launch_bounds__(256)
+add_layernorm_kernel(const float* res, const TD* __restrict__ delta, const float* __restrict__ g0,
+                     const float* __restrict__ b0, const float* __restrict__ g1, const float* __restrict__ b1, float eps,
+                     int64_t n, int C, float* res_out, TN* __restrict__ norm_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float invC = 1.f / (float)C;
+  for (int64_t r = warp0; r < n; r += nwarp) {
+    float v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) {
+      const int c = lane + 32 * u;
+      v[u] = (c < C && delta) ? e_in<TD>(delta[(size_t)r * C + c]) : 0.f;
+      s += v[u];
+    }
+    if (g0) {
+      const float mean = warp_sum(s) * invC;
+      float q = 0.f;
+#pragma unroll
+      for (int u = 0; u < VPL; ++u) {
+        const int c = lane + 32 * u;
+        const float d = c < C ? v[u] - mean : 0.f;
+        q += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(q) * invC + eps);
+#pragma unroll
+      for (int u = 0; u < VPL; ++u) {
+        const int c = lane + 32 * u;
+        if (c < C) v[u] = (v[u] - mean) * rstd * g0[c] + b0[c];
+      }
+    }
+    s = 0.f;
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) {
+      const int c = lane + 32 * u;
+      if (c < C) {
+        if (res) v[u] += res[(size_t)r * C + c];
+        if (res_out) res_out[(size_t)r * C + c] = v[u];
+        s += v[u];
+      }
+    }
+    if (norm_out) {
+      if (g1) {
+        const float mean = warp_sum(s) * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          const int c = lane + 32 * u;
+          const float d = c < C ? v[u] - mean : 0.f;
+          q += d * d;
+        }
+        const float rstd = rsqrtf(warp_sum(q) * invC + eps);
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          const int c = lane + 32 * u;
+          if (c < C) norm_out[(size_t)r * C + c] = e_out<TN>((v[u] - mean) * rstd * g1[c] + b1[c]);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+          const int c = lane + 32 * u;
+          if (c < C) norm_out[(size_t)r * C + c] = e_out<TN>(v[u]);
+        }
+      }
+    }
+  }
+}
+
+// out = act(x * scale[c] + shift[c]);  act: 0 none, 1 GELU(erf).  scale/shift nullable (pure activation).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+affine_act_kernel(const TI* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                  int64_t total, int C, TO* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = e_in<TI>(x[i]);
+    if (scale) {
+      const int c = (int)(i % C);
+      v = v * scale[c] + shift[c];
+    }
+    if (act == 1) v = e_gelu(v);
+    out[i] = e_out<TO>(v);
+  }
+}
+
+// bf16 x 8 vectorised GELU (the MLP hidden activation, N x 4C elements)
+__global__ void __launch_bounds__(256) gelu_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    uint4 v = x[i];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float2 f = __bfloat1622float2(h[u]);
+      f.x = e_gelu(f.x);
+      f.y = e_gelu(f.y);
+      h[u] = __floats2bfloat162_rn(f.x, f.y);
+    }
+    out[i] = v;
+  }
+}
+
+// out[r, :] = x[r, :] / max(||x[r, :]||_2, eps)   (F.normalize, p = 2, dim = 1)
+template <typename TI, typename TO, int VPL>
+__global__ void __launch_bounds__(256)
+l2_normalize_kernel(const TI* __restrict__ x, int64_t n, int C, float eps, TO* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n; r += nwarp) {
+    float v[VPL];
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) {
+      const int c = lane + 32 * u;
+      v[u] = c < C ? e_in<TI>(x[(size_t)r * C + c]) : 0.f;
+      q += v[u] * v[u];
+    }
+    const float inv = 1.f / fmaxf(sqrtf(warp_sum(q)), eps);
+#pragma unroll
+    for (int u = 0; u < VPL; ++u) {
+      const int c = lane + 32 * u;
+      if (c < C) out[(size_t)r * C + c] = e_out<TO>(v[u] * inv);
+    }
+  }
+}
+
+}  // namespace ss
+
+extern "C" {
+
+int ss_add_layernorm(const float* res, const void* delta, int delta_is_bf16, const float* g0, const float* b0,
+                     const float* g1, const float* b1, float eps, int64_t n, int channels, float* res_out,
+                     void* norm_out, int norm_is_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || channels < 1 || channels > 32 * ss::kMaxPerLane || (g0 && !b0) || (g1 && !b1)) return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if ((!res && !delta) || (!res_out && !norm_out)) return SS_BAD_ARGS;
+  const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8), 32 * ss::kNumSMs);
+  const int vpl = (channels + 31) / 32;
+#define SS_LN_(TD, TN, V)                                                                                         \
+  ss::add_layernorm_kernel<TD, TN, V><<<blocks, 256, 0, stream>>>(res, (const TD*)delta, g0, b0, g1, b1, eps, n, \
+                                                                  channels, res_out, (TN*)norm_out)
+#define SS_LN_V_(TD, TN)                        \
+  do {                                          \
+    if (vpl <= 1) SS_LN_(TD, TN, 1);            \
+    else if (vpl <= 2) SS_LN_(TD, TN, 2);       \
+    else if (vpl <= 4) SS_LN_(TD, TN, 4);       \
+    else if (vpl <= 8) SS_LN_(TD, TN, 8);       \
+    else if (vpl <= 16) SS_LN_(TD, TN, 16);     \
+    else if (vpl <= 24) SS_LN_(TD, TN, 24);     \
+    else SS_LN_(TD, TN, 32);                    \
+  } while (0)
+  if (delta_is_bf16 && norm_is_bf16) SS_LN_V_(__nv_bfloat16, __nv_bfloat16);
+  else if (delta_is_bf16) SS_LN_V_(__nv_bfloat16, float);
+  else if (norm_is_bf16) SS_LN_V_(float, __nv_bfloat16);
+  else SS_LN_V_(float, float);
+#undef SS_LN_V_
+#undef SS_LN_
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+int ss_affine_act(const void* x, int in_is_bf16, const float* scale, const float* shift, int act, int64_t n,
+                  int channels, void* out, int out_is_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || channels < 1 || (scale && !shift)) return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if (!x || !out) return SS_BAD_ARGS;
+  const int64_t total = n * channels;
+  if (in_is_bf16 && out_is_bf16 && !scale && act == 1 && total % 8 == 0 && ((uintptr_t)x | (uintptr_t)out) % 16 == 0) {
+    const int64_t nvec = total / 8;
+    const int blocks = (int)ss::imin64(ss::ceil_div64(nvec, 256), 32 * ss::kNumSMs);
+    ss::gelu_bf16x8_kernel<<<blocks, 256, 0, stream>>>((const uint4*)x, (uint4*)out, nvec);
+    SS_CHECK_LAUNCH();
+    return SS_OK;
+  }
+  const int blocks = (int)ss::imin64(ss::ceil_div64(total, 256), 32 * ss::kNumSMs);
+  if (in_is_bf16 && out_is_bf16)
+    ss::affine_act_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)x, scale, shift, act, total, channels, (__nv_bfloat16*)out);
+  else if (in_is_bf16)
+    ss::affine_act_kernel<__nv_bfloat16, float><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, scale, shift, act,
+                                                                            total, channels, (float*)out);
+  else if (out_is_bf16)
+    ss::affine_act_kernel<float, __nv_bfloat16><<<blocks, 256, 0, stream>>>((const float*)x, scale, shift, act, total,
+                                                                            channels, (__nv_bfloat16*)out);
+  else
+    ss::affine_act_kernel<float, float><<<blocks, 256, 0, stream>>>((const float*)x, scale, shift, act, total, channels,
+                                                                    (float*)out);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+int ss_l2_normalize(const void* x, int in_is_bf16, int64_t n, int channels, float eps, void* out, int out_is_bf16,
+                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || channels < 1 || channels > 1024) return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if (!x || !out) return SS_BAD_ARGS;
+  const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8), 32 * ss::kNumSMs);
+  const int vpl = (channels + 31) / 32;
+#define SS_NM_(TI, TO, V) \
+  ss::l2_normalize_kernel<TI, TO, V><<<blocks, 256, 0, stream>>>((const TI*)x, n, channels, eps, (TO*)out)
+#define SS_NM_V_(TI, TO)                     \
+  do {                                       \
+    if (vpl <= 4) SS_NM_(TI, TO, 4);         \
+    else if (vpl <= 8) SS_NM_(TI, TO, 8);    \
+    else if (vpl <= 16) SS_NM_(TI, TO, 16);  \
+    else if (vpl <= 24) SS_NM_(TI, TO, 24);  \
+    else SS_NM_(TI, TO, 32);                 \
+  } while (0)
+  if (in_is_bf16 && out_is_bf16) SS_NM_V_(__nv_bfloat16, __nv_bfloat16);
+  else if (in_is_bf16) SS_NM_V_(__nv_bfloat16, float);
+  else if (out_is_bf16) SS_NM_V_(float, __nv_bfloat16);
+  else SS_NM_V_(float, float);
+#undef SS_NM_V_
+#undef SS_NM_
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+// Kernel map (neighbour table) of a submanifold k^3 convolution, built from the SORTED serialization
+// keys: every voxel looks its neighbours up by binary search in the sorted code row it already has
+// (no hash table).  Only half of the taps are searched; the mirrored tap is filled through the
+// symmetry nbr[t][p] = q  <=>  nbr[k^3-1-t][q] = p.
+//
+// Replaces (reference): the indice-pair build inside spconv.SubMConv3d
+// (call sites point_transformer_v3m1_base.py:277-284, :499-506; tensor built structure.py:131-138).
+// tap t = (i*k + j)*k + l  <->  offset (i-r, j-r, l-r) on (x, y, z);  nbr is tap-major [k^3][n] int32.
+#include "runs.cuh"
+#include "../../include/scenesplat_b200.h"
+
+namespace ss {
+
+__global__ void __launch_bounds__(256)
+sorted_keys_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ order, int64_t n,
+                   uint64_t* __restrict__ skeys) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+    skeys[j] = (uint64_t)code[order[j]];
+}
+
+template <typename CoordT>
+__global__ void __launch_bounds__(256)
+kmap_search_kernel(const CoordT* __restrict__ grid_coord, const int64_t* __restrict__ batch,
+                   const int64_t* __restrict__ order, const uint64_t* __restrict__ skeys, int64_t n, int depth,
+                   int order_id, int k, int32_t* __restrict__ nbr, unsigned long long* __restrict__ tap_count) {
+  extern __shared__ unsigned int s_cnt[];  // [k^3 / 2]
+  const int k3 = k * k * k, half = k3 / 2, r = k / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) s_cnt[i] = 0u;
+  __syncthreads();
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = j < n;
+  int64_t p = 0;
+  int x = 0, y = 0, z = 0;
+  uint64_t bpart = 0;
+  if (active) {
+    p = order[j];
+    x = (int)grid_coord[p * 3 + 0];
+    y = (int)grid_coord[p * 3 + 1];
+    z = (int)grid_coord[p * 3 + 2];
+    bpart = (uint64_t)batch[p] << (3 * depth);
+    nbr[(size_t)half * n + p] = (int32_t)p;  // centre tap
+  }
+  const int lim = 1 << depth;
+  for (int t = 0; t < half; ++t) {
+    const int dx = t / (k * k) - r, dy = (t / k) % k - r, dz = t % k - r;
+    int32_t found = -1;
+    if (active) {
+      const int qx = x + dx, qy = y + dy, qz = z + dz;
+      if (qx >= 0 && qy >= 0 && qz >= 0 && qx < lim && qy < lim && qz < lim) {
+        const uint64_t key = bpart | sfc_key(order_id, (uint32_t)qx, (uint32_t)qy, (uint32_t)qz, depth);
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (skeys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        if (lo < n && skeys[lo] == key) found = (int32_t)order[lo];
+      }
+      nbr[(size_t)t * n + p] = found;
+      if (found >= 0) nbr[(size_t)(k3 - 1 - t) * n + found] = (int32_t)p;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, found >= 0);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&s_cnt[t], __popc(ballot));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const unsigned c = s_cnt[i];
+    if (c) {
+      atomicAdd(&tap_count[i], (unsigned long long)c);
+      atomicAdd(&tap_count[k3 - 1 - i], (unsigned long long)c);
+    }
+  }
+}
+
+__global__ void kmap_center_count(unsigned long long* tap_count, int half, int64_t n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) tap_count[half] = (unsigned long long)n;
+}
+
+// Pair lists for the gather-GEMM-scatter conv: along the sorted order j, for every tap t the active
+// (in, out) pairs get consecutive rows starting at tap_base[t] (host-provided, padded to the GEMM tile).
+struct PairRuns {
+  const int32_t* nbr;
+  const int64_t* order;
+  const int64_t* tap_base;  // [k3] device copy
+  int64_t n;
+  int32_t* pair_in;   // [P_pad]  input row of every Y row
+  int32_t* ypos;      // [k3][n]  Y row of (tap, output point) or -1
+  // "head" = pair is active: rank among active pairs of the tap = exclusive count of heads before j
+  __device__ bool head(int t, int64_t j) const { return nbr[(size_t)t * n + order[j]] >= 0; }
+  __device__ void emit(int t, int64_t j, uint32_t run, bool is_head) const {
+    const int64_t p = order[j];
+    if (is_head) {
+      const int64_t pos = tap_base[t] + (int64_t)run;
+      pair_in[pos] = nbr[(size_t)t * n + p];
+      ypos[(size_t)t * n + p] = (int32_t)pos;
+    } else {
+      ypos[(size_t)t * n + p] = -1;
+    }
+  }
+};
+
+}  // namespace ss
+
+extern "C" {
+
+size_t ss_kmap_workspace_bytes(int64_t n, int k) {
+  if (n < 0 || k < 1) return 0;
+  return ss::align_up((size_t)(n > 0 ? n : 1) * 8, 256) + ss::align_up(ss::runs_workspace_bytes(n, k * k * k), 256) + 512;
+}
+
+int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* batch, const int64_t* code_row,
+                  const int64_t* order_row, int64_t n, int depth, int order_id, int k, int32_t* nbr,
+                  int64_t* tap_count_dev, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || n > 0x7fffffff || depth < 1 || depth > 16 || order_id < 0 || order_id > 3 || (k != 3 && k != 5) ||
+      !tap_count_dev)
+    return SS_BAD_ARGS;
+  const int k3 = k * k * k;
+  SS_CUDA(cudaMemsetAsync(tap_count_dev, 0, (size_t)k3 * 8, stream));
+  if (n == 0) return SS_OK;
+  if (!grid_coord || !batch || !code_row || !order_row || !nbr || !workspace) return SS_BAD_ARGS;
+  if (workspace_bytes < ss_kmap_workspace_bytes(n, k) - 512) return SS_BAD_ARGS;
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  uint64_t* skeys = (uint64_t*)ws;
+  const int blocks = ss::ceil_div((int)n, 256);
+  ss::sorted_keys_kernel<<<min(blocks, 16 * ss::kNumSMs), 256, 0, stream>>>(code_row, order_row, n, skeys);
+  // mirrored half (taps > centre) is only written where a neighbour exists
+  SS_CUDA(cudaMemsetAsync(nbr + (size_t)(k3 / 2 + 1) * n, 0xff, (size_t)(k3 / 2) * n * 4, stream));
+  const size_t smem = (size_t)(k3 / 2) * 4;
+  if (coord_is_int32)
+    ss::kmap_search_kernel<int><<<blocks, 256, smem, stream>>>((const int*)grid_coord, batch, order_row, skeys, n, depth,
+                                                              order_id, k, nbr, (unsigned long long*)tap_count_dev);
+  else
+    ss::kmap_search_kernel<long long><<<blocks, 256, smem, stream>>>((const long long*)grid_coord, batch, order_row, skeys,
+                                                                    n, depth, order_id, k, nbr,
+                                                                    (unsigned long long*)tap_count_dev);
+  SS_CHECK_LAUNCH();
+  ss::kmap_center_count<<<1, 32, 0, stream>>>((unsigned long long*)tap_count_dev, k3 / 2, n);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k, const int64_t* tap_base_dev,
+                  int64_t p_pad, int32_t* pair_in, int32_t* ypos, void* workspace, size_t workspace_bytes,
+                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || (k != 3 && k != 5) || p_pad < 0) return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if (!nbr || !order_row || !tap_base_dev || !pair_in || !ypos || !workspace) return SS_BAD_ARGS;
+  // padding rows of every tap segment gather row 0 (their products are never read back)
+  SS_CUDA(cudaMemsetAsync(pair_in, 0, (size_t)p_pad * 4, stream));
+  if (workspace_bytes < ss_kmap_workspace_bytes(n, k) - 512) return SS_BAD_ARGS;
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  ws += ss::align_up((size_t)n * 8, 256);
+  ss::PairRuns f{nbr, order_row, tap_base_dev, n, pair_in, ypos};
+  return ss::runs_launch(f, n, ws, nullptr, stream, k * k * k);
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+// SerializedPooling / SerializedUnpooling on the GPU.
+//
+// Replaces (reference): pointcept/models/point_transformer_v3/point_transformer_v3m1_base.py:384-428
+// (torch.unique + torch.sort + argsort x4 + scatter_ + torch_scatter.segment_csr) and :471-482.
+//
+// Key fact: the parent's `order[0]` already sorts by `code[0]`, and all members of a
+// cluster share `code[r] >> 3` in every row r, so clusters are contiguous runs along EVERY parent
+// order row.  Cluster ids, counts, the pooled codes AND the pooled order/inverse of all rows
+// therefore come out of run-length scans -- no sort, no unique.
+#include "runs.cuh"
+#include "../../include/scenesplat_b200.h"
+
+namespace ss {
+
+struct PoolRow0 {
+  const int64_t* code;   // parent [k][n]
+  const int64_t* order;  // parent [k][n]
+  const int64_t* grid_coord;  // parent [n][3] (nullable)
+  const int64_t* batch;       // parent [n] (nullable)
+  int64_t n;
+  int k;
+  int shift;  // 3 * pooling_depth
+  int pool_depth;
+  int4 src_row;  // child row r' <- parent row src_row[r']
+  int64_t m_cap;  // row stride of the child arrays
+  int64_t* cluster;   // [n]
+  int64_t* seg_start; // [n+1]
+  int64_t* head_idx;  // [m_cap]
+  int64_t* ccode;     // child [k][m_cap]
+  int64_t* corder;
+  int64_t* cinverse;
+  int64_t* cgrid;     // [m_cap][3]
+  int64_t* cbatch;    // [m_cap]
+  __device__ bool head(int, int64_t j) const {
+    return j == 0 || (code[order[j]] >> shift) != (code[order[j - 1]] >> shift);
+  }
+  __device__ void emit(int, int64_t j, uint32_t run, bool is_head) const {
+    const int64_t p = order[j];
+    cluster[p] = (int64_t)run;
+    if (is_head) {
+      seg_start[run] = j;
+      head_idx[run] = p;
+      const int rows[4] = {src_row.x, src_row.y, src_row.z, src_row.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (r < k) {
+          ccode[(size_t)r * m_cap + run] = code[(size_t)rows[r] * n + p] >> shift;
+          if (rows[r] == 0) {
+            corder[(size_t)r * m_cap + run] = (int64_t)run;
+            cinverse[(size_t)r * m_cap + run] = (int64_t)run;
+          }
+        }
+      }
+      if (cgrid) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) cgrid[(size_t)run * 3 + a] = grid_coord[p * 3 + a] >> pool_depth;
+      }
+      if (cbatch) cbatch[run] = batch[p];
+    }
+  }
+};
+
+struct PoolRowsN {
+  const int64_t* code;
+  const int64_t* order;
+  const int64_t* cluster;
+  int64_t n;
+  int shift;
+  int rows_parent[4];  // blockIdx.y -> parent row
+  int rows_child[4];   // blockIdx.y -> child row
+  int64_t m_cap;
+  int64_t* corder;
+  int64_t* cinverse;
+  __device__ bool head(int y, int64_t j) const {
+    const int64_t* c = code + (size_t)rows_parent[y] * n;
+    const int64_t* o = order + (size_t)rows_parent[y] * n;
+    return j == 0 || (c[o[j]] >> shift) != (c[o[j - 1]] >> shift);
+  }
+  __device__ void emit(int y, int64_t j, uint32_t run, bool is_head) const {
+    if (!is_head) return;
+    const int64_t c = cluster[order[(size_t)rows_parent[y] * n + j]];
+    corder[(size_t)rows_child[y] * m_cap + run] = c;
+    cinverse[(size_t)rows_child[y] * m_cap + c] = (int64_t)run;
+  }
+};
+
+__global__ void pool_close_start(int64_t* start, const int64_t* m, int64_t n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) start[*m] = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+// One warp per segment (grid-stride).  out[s, :] = reduce_{j in [start[s], start[s+1])} src[order[j], :]
+// then optional per-channel affine (eval-mode BatchNorm folded to scale/shift) and GELU.
+// reduce: 0 = sum, 1 = mean, 2 = max, 3 = min
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+segment_reduce_kernel(const TI* __restrict__ src, const int64_t* __restrict__ order, const int64_t* __restrict__ start,
+                      const int64_t* __restrict__ m_dev, int64_t m, int C, int reduce, const float* __restrict__ scale,
+                      const float* __restrict__ shift, int act, TO* __restrict__ out) {
+  const int64_t M = m_dev ? *m_dev : m;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = warp0; s < M; s += nwarp) {
+    const int64_t a = start[s], b = start[s + 1];
+    for (int c0 = 0; c0 < C; c0 += 128) {  // each lane owns up to 4 channels per sweep (c0 + lane + 32*u)
+      float acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = reduce == 2 ? -INFINITY : (reduce == 3 ? INFINITY : 0.f);
+      for (int64_t j = a; j < b; ++j) {
+        const TI* row = src + (size_t)order[j] * C;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + lane + 32 * u;
+          if (c < C) {
+            const float v = to_f<TI>(row[c]);
+            acc[u] = reduce == 2 ? fmaxf(acc[u], v) : (reduce == 3 ? fminf(acc[u], v) : acc[u] + v);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + lane + 32 * u;
+        if (c < C) {
+          float v = acc[u];
+          if (reduce == 1) v = v / (float)(b - a);
+          if (scale) v = v * scale[c] + shift[c];
+          if (act == 1) v = gelu_erf(v);
+          out[(size_t)s * C + c] = from_f<TO>(v);
+        }
+      }
+    }
+  }
+}
+
+// out[i, :] = f(a[i, :]) + f(b[cluster[i], :]),  f = optional affine (folded BN) + GELU per branch.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+unpool_kernel(const TI* __restrict__ a, const TI* __restrict__ b, const int64_t* __restrict__ cluster, int64_t n, int C,
+              const float* __restrict__ sa, const float* __restrict__ ta, const float* __restrict__ sb,
+              const float* __restrict__ tb, int act, TO* __restrict__ out, TO* __restrict__ out_a) {
+  const int64_t total = n * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    float va = to_f<TI>(a[i]);
+    float vb = to_f<TI>(b[(size_t)cluster[r] * C + c]);
+    if (sa) va = va * sa[c] + ta[c];
+    if (sb) vb = vb * sb[c] + tb[c];
+    if (act == 1) {
+      va = gelu_erf(va);
+      vb = gelu_erf(vb);
+    }
+    out[i] = from_f<TO>(va + vb);
+    if (out_a) out_a[i] = from_f<TO>(va);
+  }
+}
+
+}  // namespace ss
+
+extern "C" {
+
+size_t ss_pool_workspace_bytes(int64_t n) { return ss::align_up(ss::runs_workspace_bytes(n, 4), 256) * 2 + 256; }
+
+int ss_pool_index(const int64_t* code, const int64_t* order, const int64_t* grid_coord, const int64_t* batch, int64_t n,
+                  int k, int pooling_depth, const int* src_row, int64_t m_cap, int64_t* cluster, int64_t* seg_start,
+                  int64_t* head, int64_t* m_dev, int64_t* child_code, int64_t* child_order, int64_t* child_inverse,
+                  int64_t* child_grid_coord, int64_t* child_batch, void* workspace, size_t workspace_bytes,
+                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || k < 1 || k > 4 || pooling_depth < 0 || pooling_depth > 16 || m_cap < n || !src_row || !m_dev)
+    return SS_BAD_ARGS;
+  if (n == 0) {
+    SS_CUDA(cudaMemsetAsync(m_dev, 0, 8, stream));
+    return SS_OK;
+  }
+  if (!code || !order || !cluster || !seg_start || !head || !child_code || !child_order || !child_inverse || !workspace)
+    return SS_BAD_ARGS;
+  if (workspace_bytes < ss_pool_workspace_bytes(n) - 256) return SS_BAD_ARGS;
+  bool has0 = false;
+  for (int r = 0; r < k; ++r) {
+    if (src_row[r] < 0 || src_row[r] >= k) return SS_BAD_ARGS;
+    has0 |= src_row[r] == 0;
+  }
+  (void)has0;
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  ss::PoolRow0 f0;
+  f0.code = code; f0.order = order; f0.grid_coord = grid_coord; f0.batch = batch; f0.n = n; f0.k = k;
+  f0.shift = 3 * pooling_depth; f0.pool_depth = pooling_depth;
+  f0.src_row = make_int4(src_row[0], k > 1 ? src_row[1] : 0, k > 2 ? src_row[2] : 0, k > 3 ? src_row[3] : 0);
+  f0.m_cap = m_cap; f0.cluster = cluster; f0.seg_start = seg_start; f0.head_idx = head; f0.ccode = child_code;
+  f0.corder = child_order; f0.cinverse = child_inverse; f0.cgrid = child_grid_coord; f0.cbatch = child_batch;
+  int rc = ss::runs_launch(f0, n, ws, m_dev, stream, 1);
+  if (rc) return rc;
+  ss::pool_close_start<<<1, 32, 0, stream>>>(seg_start, m_dev, n);
+  ss::PoolRowsN fn;
+  fn.code = code; fn.order = order; fn.cluster = cluster; fn.n = n; fn.shift = 3 * pooling_depth; fn.m_cap = m_cap;
+  fn.corder = child_order; fn.cinverse = child_inverse;
+  int rows = 0;
+  for (int r = 0; r < k; ++r)
+    if (src_row[r] != 0) {
+      fn.rows_parent[rows] = src_row[r];
+      fn.rows_child[rows] = r;
+      ++rows;
+    }
+  if (rows > 0) {
+    rc = ss::runs_launch(fn, n, ws + ss::align_up(ss::runs_workspace_bytes(n, 4), 256), nullptr, stream, rows);
+    if (rc) return rc;
+  }
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+int ss_segment_reduce(const void* src, int src_is_bf16, const int64_t* order, const int64_t* seg_start,
+                      const int64_t* m_dev, int64_t m, int channels, int reduce, const float* scale, const float* shift,
+                      int act, void* out, int out_is_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (m < 0 || channels < 1 || reduce < 0 || reduce > 3 || (scale && !shift)) return SS_BAD_ARGS;
+  if (m == 0) return SS_OK;
+  if (!src || !order || !seg_start || !out) return SS_BAD_ARGS;
+  const int blocks = (int)ss::imin64(ss::ceil_div64(m, 8), 16 * ss::kNumSMs);
+  if (src_is_bf16 && out_is_bf16)
+    ss::segment_reduce_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)src, order, seg_start, m_dev, m, channels, reduce, scale, shift, act, (__nv_bfloat16*)out);
+  else if (src_is_bf16)
+    ss::segment_reduce_kernel<__nv_bfloat16, float><<<blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)src, order, seg_start, m_dev, m, channels, reduce, scale, shift, act, (float*)out);
+  else if (out_is_bf16)
+    ss::segment_reduce_kernel<float, __nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        (const float*)src, order, seg_start, m_dev, m, channels, reduce, scale, shift, act, (__nv_bfloat16*)out);
+  else
+    ss::segment_reduce_kernel<float, float><<<blocks, 256, 0, stream>>>(
+        (const float*)src, order, seg_start, m_dev, m, channels, reduce, scale, shift, act, (float*)out);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+int ss_unpool_gather_add(const void* a, const void* b, int in_is_bf16, const int64_t* cluster, int64_t n, int channels,
+                         const float* scale_a, const float* shift_a, const float* scale_b, const float* shift_b, int act,
+                         void* out, void* out_a, int out_is_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || channels < 1 || (scale_a && !shift_a) || (scale_b && !shift_b)) return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if (!a || !b || !cluster || !out) return SS_BAD_ARGS;
+  const int blocks = (int)ss::imin64(ss::ceil_div64(n * channels, 256), 16 * ss::kNumSMs);
+  if (in_is_bf16 && out_is_bf16)
+    ss::unpool_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, cluster, n, channels, scale_a, shift_a, scale_b, shift_b, act,
+        (__nv_bfloat16*)out, (__nv_bfloat16*)out_a);
+  else if (in_is_bf16)
+    ss::unpool_kernel<__nv_bfloat16, float><<<blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, cluster, n, channels, scale_a, shift_a, scale_b, shift_b, act,
+        (float*)out, (float*)out_a);
+  else if (out_is_bf16)
+    ss::unpool_kernel<float, __nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        (const float*)a, (const float*)b, cluster, n, channels, scale_a, shift_a, scale_b, shift_b, act,
+        (__nv_bfloat16*)out, (__nv_bfloat16*)out_a);
+  else
+    ss::unpool_kernel<float, float><<<blocks, 256, 0, stream>>>((const float*)a, (const float*)b, cluster, n, channels,
+                                                                scale_a, shift_a, scale_b, shift_b, act, (float*)out,
+                                                                (float*)out_a);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+}  // extern "C"

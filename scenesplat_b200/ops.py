@@ -1,0 +1,321 @@
+"""Tensor-level wrappers over the C-ABI kernels: allocate outputs with torch, pass raw pointers.
+
+Every function here runs on the current CUDA stream and never falls back to torch ops for the
+computation itself (the CUDA library is the only implementation).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+ORDER_IDS = {"z": 0, "z-trans": 1, "hilbert": 2, "hilbert-trans": 3}
+_BF16 = torch.bfloat16
+
+
+def _isbf(t):
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise L.CudaKernelError(f"unsupported dtype {t.dtype} (float32 or bfloat16)")
+
+
+def _i64(t):
+    return t if t.dtype == torch.int64 else t.long()
+
+
+# ------------------------------------------------------------------------------------------- serialization
+def coord_depth(grid_coord: torch.Tensor) -> int:
+    """depth = bit_length(max grid_coord) (structure.py:66).  One 8-byte D2H read."""
+    g = grid_coord.contiguous()
+    out = torch.empty(1, dtype=torch.int64, device=g.device)
+    L.call("ss_coord_max", L.ptr(g), int(g.dtype == torch.int32), g.shape[0], L.ptr(out), L.stream())
+    return max(int(out.item()).bit_length(), 1)
+
+
+def serialize(grid_coord, offset, depth: int, orders, want_batch=True):
+    """-> (batch [n] or None, code [k,n], order [k,n], inverse [k,n]) int64."""
+    g = grid_coord.contiguous()
+    if g.dtype not in (torch.int64, torch.int32):
+        g = g.long()
+    offset = _i64(offset).contiguous()
+    n, k = g.shape[0], len(orders)
+    dev = g.device
+    ids = L.int_array([ORDER_IDS[o] if isinstance(o, str) else int(o) for o in orders])
+    code = torch.empty((k, n), dtype=torch.int64, device=dev)
+    order = torch.empty((k, n), dtype=torch.int64, device=dev)
+    inverse = torch.empty((k, n), dtype=torch.int64, device=dev)
+    batch = torch.empty(n, dtype=torch.int64, device=dev) if want_batch else None
+    nb = offset.numel()
+    wsb = L.load().ss_serialize_workspace_bytes(n, k, depth, nb)
+    ws = L.workspace(wsb, dev)
+    L.call("ss_serialize", L.ptr(g), int(g.dtype == torch.int32), L.ptr(offset), nb, n, depth, k, ids, L.ptr(batch),
+           L.ptr(code), L.ptr(order), L.ptr(inverse), L.ptr(ws), ws.numel(), L.stream())
+    return batch, code, order, inverse
+
+
+# ------------------------------------------------------------------------------------------- GridSample
+def gridsample_index(coord, grid_size: float, hash_type: str = "fnv"):
+    """-> dict(idx_sort, inverse, start, m (python int; one D2H read), m_dev, min_coord)."""
+    coord = coord.contiguous().float()
+    n, dev = coord.shape[0], coord.device
+    idx_sort = torch.empty(n, dtype=torch.int64, device=dev)
+    inverse = torch.empty(n, dtype=torch.int64, device=dev)
+    start = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    m_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    mn = torch.zeros(3, dtype=torch.int64, device=dev)
+    ws = L.workspace(L.load().ss_gridsample_workspace_bytes(n), dev)
+    L.call("ss_gridsample_index", L.ptr(coord), n, float(grid_size), 0 if hash_type == "fnv" else 1, L.ptr(idx_sort),
+           L.ptr(inverse), L.ptr(start), L.ptr(m_dev), L.ptr(mn), L.ptr(ws), ws.numel(), L.stream())
+    m = int(m_dev.item())
+    return dict(coord=coord, idx_sort=idx_sort, inverse=inverse, start=start, m=m, m_dev=m_dev, min_coord=mn,
+                grid_size=float(grid_size))
+
+
+def gridsample_select(ix, rnd=None, frag: int = 0, want_grid_coord=True, want_count=False):
+    coord = ix["coord"]
+    n, m, dev = coord.shape[0], ix["m"], coord.device
+    idx_unique = torch.empty(m, dtype=torch.int64, device=dev)
+    gc = torch.empty((m, 3), dtype=torch.int64, device=dev) if want_grid_coord else None
+    cnt = torch.empty(m, dtype=torch.int64, device=dev) if want_count else None
+    if rnd is not None:
+        rnd = _i64(rnd).contiguous()
+    L.call("ss_gridsample_select", L.ptr(coord), n, ix["grid_size"], L.ptr(ix["min_coord"]), L.ptr(ix["idx_sort"]),
+           L.ptr(ix["start"]), L.ptr(ix["m_dev"]), L.ptr(rnd), int(frag), L.ptr(idx_unique), L.ptr(gc), L.ptr(cnt),
+           L.stream())
+    return idx_unique, gc, cnt
+
+
+def gather_rows(src, idx):
+    src = src.contiguous()
+    m = idx.shape[0]
+    out = torch.empty((m,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    row_bytes = src.element_size() * (src[0].numel() if src.dim() > 1 else 1)
+    L.call("ss_gather_rows", L.ptr(src), row_bytes, L.ptr(idx), None, m, L.ptr(out), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- pooling
+def pool_index(code, order, grid_coord, batch, pooling_depth: int, src_row):
+    """-> dict(cluster, seg_start, head, m, code, order, inverse, grid_coord, batch) (children sliced to m)."""
+    k, n = code.shape
+    dev = code.device
+    cluster = torch.empty(n, dtype=torch.int64, device=dev)
+    seg_start = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    head = torch.empty(n, dtype=torch.int64, device=dev)
+    m_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    ccode = torch.empty((k, n), dtype=torch.int64, device=dev)
+    corder = torch.empty((k, n), dtype=torch.int64, device=dev)
+    cinv = torch.empty((k, n), dtype=torch.int64, device=dev)
+    gc = _i64(grid_coord).contiguous() if grid_coord is not None else None
+    cgc = torch.empty((n, 3), dtype=torch.int64, device=dev) if gc is not None else None
+    cb = torch.empty(n, dtype=torch.int64, device=dev) if batch is not None else None
+    ws = L.workspace(L.load().ss_pool_workspace_bytes(n), dev)
+    L.call("ss_pool_index", L.ptr(code.contiguous()), L.ptr(order.contiguous()), L.ptr(gc),
+           L.ptr(batch.contiguous() if batch is not None else None), n, k, pooling_depth, L.int_array(src_row), n,
+           L.ptr(cluster), L.ptr(seg_start), L.ptr(head), L.ptr(m_dev), L.ptr(ccode), L.ptr(corder), L.ptr(cinv),
+           L.ptr(cgc), L.ptr(cb), L.ptr(ws), ws.numel(), L.stream())
+    m = int(m_dev.item())
+    return dict(cluster=cluster, seg_start=seg_start[: m + 1], head=head[:m], m=m,
+                code=ccode[:, :m].contiguous(), order=corder[:, :m].contiguous(), inverse=cinv[:, :m].contiguous(),
+                grid_coord=cgc[:m] if cgc is not None else None, batch=cb[:m] if cb is not None else None)
+
+
+_REDUCE = {"sum": 0, "mean": 1, "max": 2, "min": 3}
+
+
+def segment_reduce(src, order_row, seg_start, reduce="mean", scale=None, shift=None, act=0, out_dtype=None):
+    src = src.contiguous()
+    m = seg_start.shape[0] - 1
+    c = src.shape[1]
+    out = torch.empty((m, c), dtype=out_dtype or src.dtype, device=src.device)
+    L.call("ss_segment_reduce", L.ptr(src), _isbf(src), L.ptr(order_row), L.ptr(seg_start), None, m, c,
+           _REDUCE[reduce], L.ptr(scale), L.ptr(shift), act, L.ptr(out), _isbf(out), L.stream())
+    return out
+
+
+def unpool_gather_add(a, b, cluster, scale_a=None, shift_a=None, scale_b=None, shift_b=None, act=0, out_dtype=None,
+                      want_a=False):
+    a, b = a.contiguous(), b.contiguous()
+    n, c = a.shape
+    od = out_dtype or a.dtype
+    out = torch.empty((n, c), dtype=od, device=a.device)
+    out_a = torch.empty((n, c), dtype=od, device=a.device) if want_a else None
+    L.call("ss_unpool_gather_add", L.ptr(a), L.ptr(b), _isbf(a), L.ptr(cluster), n, c, L.ptr(scale_a), L.ptr(shift_a),
+           L.ptr(scale_b), L.ptr(shift_b), act, L.ptr(out), L.ptr(out_a), _isbf(out), L.stream())
+    return out, out_a
+
+
+# ------------------------------------------------------------------------------------------- submanifold conv
+def kmap_build(grid_coord, batch, code_row, order_row, depth: int, order_id: int, k: int):
+    """-> (nbr [k^3, n] int32, tap_count [k^3] int64 device)."""
+    g = grid_coord.contiguous()
+    if g.dtype not in (torch.int64, torch.int32):
+        g = g.long()
+    n, dev = g.shape[0], g.device
+    k3 = k ** 3
+    nbr = torch.empty((k3, n), dtype=torch.int32, device=dev)
+    cnt = torch.empty(k3, dtype=torch.int64, device=dev)
+    ws = L.workspace(L.load().ss_kmap_workspace_bytes(n, k), dev)
+    L.call("ss_kmap_build", L.ptr(g), int(g.dtype == torch.int32), L.ptr(batch.contiguous()),
+           L.ptr(code_row.contiguous()), L.ptr(order_row.contiguous()), n, depth, order_id, k, L.ptr(nbr), L.ptr(cnt),
+           L.ptr(ws), ws.numel(), L.stream())
+    return nbr, cnt
+
+
+def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = 128):
+    """Pair lists for the gather-GEMM conv.  -> dict(pair_in [p_pad] i32, ypos [k^3, n] i32, tile_tap [p_pad/tile] i32,
+    p_pad, pairs)."""
+    k3, n = nbr.shape
+    dev = nbr.device
+    base, tile_tap, o = [], [], 0
+    for t in range(k3):
+        base.append(o)
+        nt = (int(tap_count_host[t]) + tile - 1) // tile
+        tile_tap += [t] * nt
+        o += nt * tile
+    p_pad = o
+    base_dev = torch.tensor(base, dtype=torch.int64, device=dev)
+    pair_in = torch.empty(max(p_pad, 1), dtype=torch.int32, device=dev)
+    ypos = torch.empty((k3, n), dtype=torch.int32, device=dev)
+    ws = L.workspace(L.load().ss_kmap_workspace_bytes(n, k), dev)
+    L.call("ss_kmap_pairs", L.ptr(nbr), L.ptr(order_row.contiguous()), n, k, L.ptr(base_dev), p_pad, L.ptr(pair_in),
+           L.ptr(ypos), L.ptr(ws), ws.numel(), L.stream())
+    return dict(pair_in=pair_in, ypos=ypos, tile_tap=torch.tensor(tile_tap or [0], dtype=torch.int32, device=dev),
+                p_pad=p_pad, pairs=int(sum(int(c) for c in tap_count_host)))
+
+
+def subm_conv_simt(x, nbr, wt, bias=None, scale=None, shift=None, act=0, out_dtype=None):
+    """wt: [k^3, cin, cout] fp32."""
+    x = x.contiguous()
+    k3, n = nbr.shape
+    cin, cout = wt.shape[1], wt.shape[2]
+    out = torch.empty((n, cout), dtype=out_dtype or x.dtype, device=x.device)
+    L.call("ss_subm_conv_simt", L.ptr(x), _isbf(x), L.ptr(nbr), L.ptr(wt), L.ptr(bias), L.ptr(scale), L.ptr(shift), act,
+           n, k3, cin, cout, L.ptr(out), _isbf(out), L.stream())
+    return out
+
+
+def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16):
+    """tcgen05 gather-GEMM (+ gather-sum).  w_bf16: [k^3, cout, cin] bf16."""
+    k3, cout, cin = w_bf16.shape
+    p_pad = pairs["p_pad"]
+    prod = torch.empty((max(p_pad, 1), cout), dtype=_BF16, device=x_bf16.device)
+    L.call("ss_subm_conv_gemm", L.ptr(x_bf16.contiguous()), L.ptr(pairs["pair_in"]), L.ptr(w_bf16),
+           L.ptr(pairs["tile_tap"]), p_pad, k3, cin, cout, L.ptr(prod), L.stream())
+    out = torch.empty((n, cout), dtype=out_dtype, device=x_bf16.device)
+    L.call("ss_subm_conv_reduce", L.ptr(prod), L.ptr(pairs["ypos"]), L.ptr(bias), n, k3, cout, L.ptr(out), _isbf(out),
+           L.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- attention
+def patch_table(offset, patch_size: int, n_total: int):
+    offset = _i64(offset).contiguous()
+    nb = offset.numel()
+    max_patches = n_total // patch_size + nb
+    table = torch.empty((max_patches, 4), dtype=torch.int32, device=offset.device)
+    L.call("ss_patch_table", L.ptr(offset), nb, patch_size, max_patches, L.ptr(table), None, L.stream())
+    return table
+
+
+def patch_attention(qkv, order_row, table, patch_size: int, heads: int, scale: float, out_dtype=None, impl="auto"):
+    qkv = qkv.contiguous()
+    n, c3 = qkv.shape
+    c = c3 // 3
+    d = c // heads
+    out = torch.empty((n, c), dtype=out_dtype or qkv.dtype, device=qkv.device)
+    tc_ok = (qkv.dtype == _BF16 and out.dtype == _BF16 and d in (16, 32, 48, 64) and patch_size % 128 == 0
+             and patch_size <= 1024)
+    if impl == "tc" and not tc_ok:
+        raise L.CudaKernelError("tcgen05 attention needs bf16, head_dim in {16,32,48,64}, patch multiple of 128")
+    if impl == "tc":
+        L.call("ss_patch_attention", L.ptr(qkv), L.ptr(order_row), L.ptr(table), table.shape[0], patch_size, heads, d,
+               float(scale), L.ptr(out), L.stream())
+    else:
+        L.call("ss_patch_attention_simt", L.ptr(qkv), _isbf(qkv), L.ptr(order_row), L.ptr(table), table.shape[0],
+               patch_size, heads, d, float(scale), L.ptr(out), _isbf(out), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- row-wise fusions
+def add_layernorm(res, delta, ln0=None, ln1=None, eps=1e-5, want_res=True, norm_dtype=None, inplace=False):
+    """y = res + LN0(delta) (LN0 optional); returns (y fp32 or None, LN1(y) / cast(y) or None)."""
+    ref = delta if delta is not None else res
+    n, c = ref.shape
+    dev = ref.device
+    res_out = None
+    if want_res:
+        res_out = res if (inplace and res is not None) else torch.empty((n, c), dtype=torch.float32, device=dev)
+    norm_out = torch.empty((n, c), dtype=norm_dtype, device=dev) if norm_dtype is not None else None
+    g0, b0 = ln0 if ln0 is not None else (None, None)
+    g1, b1 = ln1 if ln1 is not None else (None, None)
+    L.call("ss_add_layernorm", L.ptr(res), L.ptr(delta), _isbf(delta) if delta is not None else 0, L.ptr(g0), L.ptr(b0),
+           L.ptr(g1), L.ptr(b1), float(eps), n, c, L.ptr(res_out), L.ptr(norm_out),
+           _isbf(norm_out) if norm_out is not None else 0, L.stream())
+    return res_out, norm_out
+
+
+def affine_act(x, scale=None, shift=None, act=0, out_dtype=None):
+    x = x.contiguous()
+    n, c = x.shape
+    out = torch.empty((n, c), dtype=out_dtype or x.dtype, device=x.device)
+    L.call("ss_affine_act", L.ptr(x), _isbf(x), L.ptr(scale), L.ptr(shift), act, n, c, L.ptr(out), _isbf(out), L.stream())
+    return out
+
+
+def l2_normalize(x, eps=1e-12, out_dtype=None):
+    x = x.contiguous()
+    n, c = x.shape
+    out = torch.empty((n, c), dtype=out_dtype or x.dtype, device=x.device)
+    L.call("ss_l2_normalize", L.ptr(x), _isbf(x), n, c, float(eps), L.ptr(out), _isbf(out), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- language head / losses
+def lang_head_argmax(feat, text, normalize=False, threshold=0.1):
+    feat = feat.contiguous()
+    text = text.contiguous().float()
+    n, c = feat.shape
+    mx = torch.empty(n, dtype=torch.float32, device=feat.device)
+    lab = torch.empty(n, dtype=torch.int64, device=feat.device)
+    L.call("ss_lang_head", L.ptr(feat), _isbf(feat), L.ptr(text), n, c, text.shape[0], int(normalize), float(threshold),
+           0, None, L.ptr(mx), L.ptr(lab), None, L.stream())
+    return mx, lab
+
+
+def lang_head_accumulate(feat, text, probs_accum, idx=None, normalize=False):
+    feat = feat.contiguous()
+    text = text.contiguous().float()
+    n, c = feat.shape
+    L.call("ss_lang_head", L.ptr(feat), _isbf(feat), L.ptr(text), n, c, text.shape[0], int(normalize), 0.0, 1,
+           L.ptr(idx), None, None, L.ptr(probs_accum), L.stream())
+    return probs_accum
+
+
+_TGT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def cos_l2_sums(pred, target, mask):
+    """-> double[3] device tensor: sum(1-cos), sum ||p-t||^2, n_valid."""
+    pred, target = pred.contiguous(), target.contiguous()
+    m8 = mask.contiguous().to(torch.uint8) if mask.dtype != torch.uint8 else mask.contiguous()
+    if mask.dtype == torch.bool:
+        m8 = mask.contiguous().view(torch.uint8)
+    n, c = pred.shape
+    acc = torch.empty(3, dtype=torch.float64, device=pred.device)
+    L.call("ss_cos_l2_loss", L.ptr(pred), _isbf(pred), L.ptr(target), _TGT[target.dtype], L.ptr(m8), n, c, L.ptr(acc),
+           L.stream())
+    return acc
+
+
+def class_half_sums(pred, mask, segment, half, n_classes: int):
+    pred = pred.contiguous()
+    m8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous().to(torch.uint8)
+    n, c = pred.shape
+    sums = torch.empty((n_classes * 2, c), dtype=torch.float32, device=pred.device)
+    counts = torch.empty(n_classes * 2, dtype=torch.int32, device=pred.device)
+    L.call("ss_class_half_sums", L.ptr(pred), _isbf(pred), L.ptr(m8), L.ptr(_i64(segment).contiguous()),
+           L.ptr(_i64(half).contiguous()), n, c, n_classes, L.ptr(sums), L.ptr(counts), L.stream())
+    return sums, counts

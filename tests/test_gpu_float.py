@@ -1,0 +1,165 @@
+"""GPU parity tests (through the C-ABI) of the floating-point kernels against the oracle.
+
+Tolerances (stated per test): fp32 kernels 1e-4 relative; bf16 tensor-core kernels are compared with the
+fp32 oracle evaluated on the SAME bf16-rounded inputs, so the remaining error is accumulation order +
+one bf16 rounding of the result (2^-8 relative) + bf16 rounding of the per-tap products in the conv.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import attention as oattn
+from oracle import gridsample as ogs
+from oracle import lang as olang
+from oracle import serialization as oser
+from oracle import subm_conv as oconv
+from scenesplat_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+ORDERS = oser.ORDERS
+
+
+def dev(a):
+    return torch.as_tensor(a).cuda()
+
+
+def _scene(n_raw=20000, seed=2, nb=2, L=3.0):
+    d = synthetic.chunk(n_raw, L=L, H=2.0, seed=seed)
+    res = ogs.grid_sample_train(d["coord"], 0.02)
+    g = res["grid_coord"]
+    n = g.shape[0]
+    offset = np.array([n // 3, n] if nb == 2 else [n], dtype=np.int64)
+    batch = oser.offset2batch(offset)
+    code, order, inv, depth = oser.serialization(g, batch, len(offset), ORDERS)
+    return g, batch, offset, code, order, inv, depth
+
+
+@pytest.mark.parametrize("k,cin,cout,bias", [(5, 11, 32, False), (3, 16, 16, True), (3, 32, 48, True)])
+def test_subm_conv_simt(k, cin, cout, bias):
+    from scenesplat_b200 import ops
+    g, batch, offset, code, order, inv, depth = _scene(8000)
+    torch.manual_seed(0)
+    n = g.shape[0]
+    x = torch.randn(n, cin)
+    w = torch.randn(cout, k, k, k, cin) * 0.1
+    b = torch.randn(cout) if bias else None
+    nbr_ref = oconv.kernel_map(g, batch, k)
+    want = oconv.subm_conv(x, nbr_ref, w, b)
+    nbr, _ = ops.kmap_build(dev(g), dev(batch), dev(code[0]), dev(order[0]), depth, 0, k)
+    wt = w.reshape(cout, k ** 3, cin).permute(1, 2, 0).contiguous().cuda()
+    got = ops.subm_conv_simt(x.cuda(), nbr, wt, b.cuda() if bias else None)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-4)  # fp32 kernel
+    # fused BN(eval)+GELU epilogue
+    scale, shift = torch.rand(cout) + 0.5, torch.randn(cout)
+    got2 = ops.subm_conv_simt(x.cuda(), nbr, wt, b.cuda() if bias else None, scale.cuda(), shift.cuda(), act=1)
+    np.testing.assert_allclose(got2.cpu().numpy(), F.gelu(want * scale + shift).numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("c", [32, 64, 128, 256, 768])
+def test_subm_conv_tensor_core(c):
+    from scenesplat_b200 import ops
+    g, batch, offset, code, order, inv, depth = _scene(6000 if c > 256 else 12000)
+    torch.manual_seed(1)
+    n = g.shape[0]
+    x = (torch.randn(n, c)).bfloat16()
+    w = (torch.randn(c, 3, 3, 3, c) * (1.0 / (c * 7) ** 0.5)).bfloat16()
+    b = torch.randn(c)
+    nbr_ref = oconv.kernel_map(g, batch, 3)
+    want = oconv.subm_conv(x.float(), nbr_ref, w.float(), b)
+    nbr, cnt = ops.kmap_build(dev(g), dev(batch), dev(code[0]), dev(order[0]), depth, 0, 3)
+    pairs = ops.kmap_pairs(nbr, dev(order[0]), 3, cnt.cpu().numpy())
+    wk = w.reshape(c, 27, c).permute(1, 0, 2).contiguous().cuda()  # [27, cout, cin]
+    got = ops.subm_conv_gemm(x.cuda(), pairs, wk, b.cuda(), n, out_dtype=torch.float32)
+    err = (got.cpu() - want).abs().max().item()
+    scale = want.abs().max().item()
+    # bf16 products (2^-9 relative each, up to 27 summed) + fp32 accumulate: 2e-2 of the output scale
+    assert err < 2e-2 * scale, (err, scale)
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    assert rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("H,d,K,dtype", [(2, 16, 64, torch.float32), (4, 16, 1024, torch.bfloat16),
+                                         (3, 32, 256, torch.bfloat16), (2, 48, 1024, torch.bfloat16),
+                                         (1, 8, 32, torch.float32)])
+def test_patch_attention_simt(H, d, K, dtype):
+    from scenesplat_b200 import ops
+    rng = np.random.default_rng(0)
+    offset = np.array([K // 2 + 3, K // 2 + 3 + 2 * K + 17, 4 * K + 40], dtype=np.int64)  # short, ragged, exact-ish
+    n = int(offset[-1])
+    C = H * d
+    torch.manual_seed(0)
+    qkv = torch.randn(n, 3 * C).to(dtype)
+    order = np.concatenate([rng.permutation(np.arange(a, b)) for a, b in zip([0, *offset[:-1]], offset)])
+    inverse = np.empty(n, dtype=np.int64)
+    inverse[order] = np.arange(n)
+    scale = d ** -0.5
+    want = oattn.serialized_attention_core(qkv.float(), order, inverse, offset, K, H, scale)
+    table = ops.patch_table(dev(offset), K, n)
+    got = ops.patch_attention(qkv.cuda(), dev(order), table, K, H, scale, out_dtype=torch.float32, impl="simt")
+    tol = 1e-4 if dtype == torch.float32 else 2e-3  # bf16 inputs are exact here; fp32 math; exp2 vs exp
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=tol, atol=tol)
+
+
+def test_add_layernorm_and_friends():
+    from scenesplat_b200 import ops
+    torch.manual_seed(0)
+    for C in (16, 32, 96, 256, 768):
+        n = 777
+        res, delta = torch.randn(n, C), torch.randn(n, C)
+        g0, b0, g1, b1 = torch.rand(C) + 0.5, torch.randn(C), torch.rand(C) + 0.5, torch.randn(C)
+        y = res + F.layer_norm(delta, (C,), g0, b0, 1e-5)
+        h = F.layer_norm(y, (C,), g1, b1, 1e-5)
+        ro, no = ops.add_layernorm(res.cuda(), delta.cuda(), (g0.cuda(), b0.cuda()), (g1.cuda(), b1.cuda()),
+                                   norm_dtype=torch.float32)
+        np.testing.assert_allclose(ro.cpu().numpy(), y.numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(no.cpu().numpy(), h.numpy(), rtol=1e-4, atol=1e-4)
+        # bf16 delta, no inner LN, bf16 normed output
+        db = delta.bfloat16()
+        ro, no = ops.add_layernorm(res.cuda(), db.cuda(), None, (g1.cuda(), b1.cuda()), norm_dtype=torch.bfloat16)
+        y2 = res + db.float()
+        np.testing.assert_allclose(ro.cpu().numpy(), y2.numpy(), rtol=1e-6, atol=1e-6)
+        h2 = F.layer_norm(y2, (C,), g1, b1, 1e-5)
+        np.testing.assert_allclose(no.float().cpu().numpy(), h2.numpy(), rtol=1e-2, atol=1e-2)  # bf16 output
+    x = torch.randn(1000, 64)
+    s, t = torch.rand(64) + 0.5, torch.randn(64)
+    got = ops.affine_act(x.cuda(), s.cuda(), t.cuda(), act=1)
+    np.testing.assert_allclose(got.cpu().numpy(), F.gelu(x * s + t).numpy(), rtol=1e-5, atol=1e-6)
+    xb = torch.randn(1000, 256).bfloat16()
+    got = ops.affine_act(xb.cuda(), act=1)
+    np.testing.assert_allclose(got.float().cpu().numpy(), F.gelu(xb.float()).bfloat16().float().numpy(), rtol=1e-2,
+                               atol=1e-3)
+    got = ops.l2_normalize(x.cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), F.normalize(x, dim=1).numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_lang_head_and_losses_golden(golden):
+    from scenesplat_b200 import ops
+    g = golden("losses.npz")
+    pred = torch.from_numpy(g["pred"].astype(np.float32)).cuda()
+    target16 = torch.from_numpy(g["target"]).cuda()
+    mask = torch.from_numpy(g["mask"]).cuda()
+    seg = torch.from_numpy(g["segment"]).cuda()
+    half = torch.from_numpy(g["half"]).cuda()
+    text = torch.from_numpy(g["text"]).cuda()
+    mx, lab = ops.lang_head_argmax(pred, text)
+    np.testing.assert_allclose(mx.cpu().numpy(), g["max_prob"], rtol=1e-5, atol=1e-6)  # fp32
+    np.testing.assert_array_equal(lab.cpu().numpy(), g["argmax"])
+    # accumulate variant == dense sigmoid(logits)
+    acc = torch.zeros(pred.shape[0], text.shape[0], device="cuda")
+    ops.lang_head_accumulate(pred, text, acc)
+    want = torch.sigmoid(pred @ text.t())
+    np.testing.assert_allclose(acc.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    for tgt in (target16, target16.float()):
+        a = ops.cos_l2_sums(pred, tgt, mask).cpu().numpy()
+        np.testing.assert_allclose(a[0] / a[2], g["cos"], rtol=1e-5)
+        np.testing.assert_allclose(a[1] / a[2], g["l2"], rtol=1e-5)
+        assert a[2] == g["mask"].sum()
+    sums, counts = ops.class_half_sums(pred, mask, seg, half, 6)
+    labs, A, B = olang.class_half_sums(pred.cpu(), mask.cpu(), seg.cpu(), half.cpu())
+    for i, lab_ in enumerate(labs.tolist()):
+        np.testing.assert_allclose(sums[2 * lab_].cpu().numpy(), A[i].numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(sums[2 * lab_ + 1].cpu().numpy(), B[i].numpy(), rtol=1e-4, atol=1e-5)
+    con = olang.contrastive_from_sums(torch.stack([sums[2 * l] for l in labs.tolist()]).cpu(),
+                                      torch.stack([sums[2 * l + 1] for l in labs.tolist()]).cpu(), 0.2, 0.025)
+    np.testing.assert_allclose(con.numpy(), g["con"], rtol=1e-4)

@@ -1,0 +1,242 @@
+"""GPU parity tests (through the C-ABI) of the integer / index stages: bit-exact against the oracle and
+the golden vectors generated from the reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention as oattn
+from oracle import gridsample as ogs
+from oracle import pooling as opool
+from oracle import serialization as oser
+from oracle import subm_conv as oconv
+from scenesplat_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+ORDERS = oser.ORDERS
+
+
+def dev(a):
+    return torch.as_tensor(a).cuda()
+
+
+@pytest.mark.parametrize("depth", [1, 2, 5, 9, 10, 16])
+def test_serialize_golden_codes(golden, depth):
+    from scenesplat_b200 import ops
+    g = golden("serialization.npz")
+    grid, batch, ref = g[f"grid_d{depth}"], g[f"batch_d{depth}"], g[f"code_d{depth}"]
+    offset = np.cumsum(np.bincount(batch, minlength=3))
+    b, code, order, inv = ops.serialize(dev(grid), dev(offset), depth, ORDERS)
+    np.testing.assert_array_equal(code.cpu().numpy(), ref)
+    np.testing.assert_array_equal(b.cpu().numpy(), batch)
+    _, o_order, o_inv, _ = oser.serialization(grid, batch, 3, ORDERS, depth=depth)
+    np.testing.assert_array_equal(order.cpu().numpy(), o_order)
+    np.testing.assert_array_equal(inv.cpu().numpy(), o_inv)
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_point_serialization_golden(golden, shuffle):
+    from scenesplat_b200 import ops
+    g = golden("serialization.npz")
+    tag = "shuf" if shuffle else "noshuf"
+    grid, offset = g["ps_grid"], g["ps_offset"]
+    depth = ops.coord_depth(dev(grid))
+    assert depth == int(g[f"ps_depth_{tag}"])
+    orders = [ORDERS[i] for i in g["ps_perm"]] if shuffle else ORDERS
+    _, code, order, inv = ops.serialize(dev(grid), dev(offset), depth, orders)
+    np.testing.assert_array_equal(code.cpu().numpy(), g[f"ps_code_{tag}"])
+    np.testing.assert_array_equal(order.cpu().numpy(), g[f"ps_order_{tag}"])
+    np.testing.assert_array_equal(inv.cpu().numpy(), g[f"ps_inverse_{tag}"])
+
+
+@pytest.mark.parametrize("n,nb,int32", [(1, 1, False), (255, 1, True), (2049, 3, False), (70001, 5, True),
+                                        (300000, 1, False)])
+def test_serialize_vs_oracle_sizes(n, nb, int32):
+    from scenesplat_b200 import ops
+    rng = np.random.default_rng(n)
+    grid = rng.integers(0, 700, (n, 3))
+    if n > 10:  # duplicates exercise the stable tie rule
+        grid[n // 2] = grid[0]
+    cuts = np.sort(rng.choice(np.arange(1, n), nb - 1, replace=False)) if nb > 1 else np.array([], dtype=np.int64)
+    offset = np.concatenate([cuts, [n]]).astype(np.int64)
+    batch = oser.offset2batch(offset)
+    gd = dev(grid.astype(np.int32 if int32 else np.int64))
+    depth = ops.coord_depth(gd)
+    assert depth == oser.serialization_depth(grid)
+    b, code, order, inv = ops.serialize(gd, dev(offset), depth, ORDERS)
+    o_code, o_order, o_inv, _ = oser.serialization(grid, batch, nb, ORDERS)
+    np.testing.assert_array_equal(b.cpu().numpy(), batch)
+    np.testing.assert_array_equal(code.cpu().numpy(), o_code)
+    np.testing.assert_array_equal(order.cpu().numpy(), o_order)
+    np.testing.assert_array_equal(inv.cpu().numpy(), o_inv)
+    # size-independent properties: order is a permutation sorting the code, inverse inverts it
+    c = code.gather(1, order)
+    assert bool((c[:, 1:] >= c[:, :-1]).all())
+    ar = torch.arange(n, device="cuda").expand(4, n)
+    assert bool((inv.gather(1, order) == ar).all())
+
+
+def test_serialize_empty():
+    from scenesplat_b200 import ops
+    g = torch.zeros((0, 3), dtype=torch.int64, device="cuda")
+    b, code, order, inv = ops.serialize(g, dev(np.array([0])), 1, ORDERS)
+    assert code.shape == (4, 0) and order.shape == (4, 0)
+
+
+@pytest.mark.parametrize("name", ["room", "boundary"])
+def test_gridsample_golden(golden, name):
+    from scenesplat_b200 import ops
+    g = golden("gridsample.npz")
+    coord = g[f"{name}_coord_in"]
+    ix = ops.gridsample_index(dev(coord), 0.02)
+    o = ogs.grid_sample_index(coord, 0.02)
+    assert ix["m"] == o["count"].shape[0]
+    np.testing.assert_array_equal(ix["inverse"].cpu().numpy(), g[f"{name}_inverse"])
+    np.testing.assert_array_equal(ix["idx_sort"].cpu().numpy(), o["idx_sort"])
+    np.testing.assert_array_equal(ix["start"][: ix["m"]].cpu().numpy(), o["start"])
+    np.testing.assert_array_equal(ix["min_coord"].cpu().numpy(), o["min_coord"])
+    rng = np.random.default_rng(0)
+    rnd = rng.integers(0, int(o["count"].max()), o["count"].size)
+    idx_u, gc, cnt = ops.gridsample_select(ix, dev(rnd), want_count=True)
+    ref = ogs.grid_sample_train(coord, 0.02, rnd)
+    np.testing.assert_array_equal(idx_u.cpu().numpy(), ref["idx_unique"])
+    np.testing.assert_array_equal(gc.cpu().numpy(), g[f"{name}_grid_coord"])
+    np.testing.assert_array_equal(cnt.cpu().numpy(), ref["count"])
+    # attribute gather
+    out = ops.gather_rows(dev(coord), idx_u)
+    np.testing.assert_array_equal(out.cpu().numpy(), coord[ref["idx_unique"]])
+    # test-mode fragments
+    parts, _ = ogs.grid_sample_test(coord, 0.02)
+    for i in (0, len(parts) - 1):
+        idx_f, _, _ = ops.gridsample_select(ix, None, frag=i, want_grid_coord=False)
+        np.testing.assert_array_equal(idx_f.cpu().numpy(), parts[i])
+
+
+def test_gridsample_ravel_and_large():
+    from scenesplat_b200 import ops
+    d = synthetic.chunk(200000, seed=9)
+    for ht in ("fnv", "ravel"):
+        ix = ops.gridsample_index(dev(d["coord"]), 0.02, ht)
+        o = ogs.grid_sample_index(d["coord"], 0.02, ht)
+        assert ix["m"] == o["count"].shape[0]
+        np.testing.assert_array_equal(ix["inverse"].cpu().numpy(), o["inverse"])
+        np.testing.assert_array_equal(ix["idx_sort"].cpu().numpy(), o["idx_sort"])
+    # property: inverse is constant per voxel and the number of distinct values is m
+    inv = ix["inverse"]
+    assert int(inv.max()) + 1 == ix["m"]
+
+
+def _parent(n_raw=30000, seed=4, nb=2):
+    d = synthetic.chunk(n_raw, L=3.0, H=2.0, seed=seed)
+    res = ogs.grid_sample_train(d["coord"], 0.02)
+    g = res["grid_coord"]
+    n = g.shape[0]
+    offset = np.array([n // 3, n] if nb == 2 else [n], dtype=np.int64)
+    return d["coord"][res["idx_unique"]], g, offset
+
+
+@pytest.mark.parametrize("perm", [[0, 1, 2, 3], [2, 0, 3, 1], [3, 2, 1, 0]])
+def test_pool_index_vs_oracle(perm):
+    from scenesplat_b200 import ops
+    coord, g, offset = _parent()
+    batch = oser.offset2batch(offset)
+    code, order, inv, depth = oser.serialization(g, batch, len(offset), ORDERS, perm=[1, 3, 0, 2])
+    ref = opool.pool_index(code, 1, perm=perm)
+    out = ops.pool_index(dev(code), dev(order), dev(g), dev(batch), 1, perm)
+    assert out["m"] == ref["counts"].shape[0]
+    np.testing.assert_array_equal(out["cluster"].cpu().numpy(), ref["cluster"])
+    np.testing.assert_array_equal(out["code"].cpu().numpy(), ref["code"])
+    np.testing.assert_array_equal(out["order"].cpu().numpy(), ref["order"])
+    np.testing.assert_array_equal(out["inverse"].cpu().numpy(), ref["inverse"])
+    np.testing.assert_array_equal(np.diff(out["seg_start"].cpu().numpy()), ref["counts"])
+    gc, b = opool.pooled_attrs(g, batch, ref["head"], 1)
+    np.testing.assert_array_equal(out["grid_coord"].cpu().numpy(), gc)
+    np.testing.assert_array_equal(out["batch"].cpu().numpy(), b)
+    # segment mean (fp32) of features and coords
+    rng = np.random.default_rng(0)
+    feat = rng.normal(size=(g.shape[0], 64)).astype(np.float32)
+    want = opool.segment_csr(feat, ref["indices"], ref["idx_ptr"], "mean")
+    got = ops.segment_reduce(dev(feat), dev(order[0]), out["seg_start"], "mean")
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    wantc = opool.segment_csr(coord, ref["indices"], ref["idx_ptr"], "mean")
+    gotc = ops.segment_reduce(dev(coord), dev(order[0]), out["seg_start"], "mean")
+    np.testing.assert_allclose(gotc.cpu().numpy(), wantc, rtol=1e-5, atol=1e-6)
+    for red in ("sum", "max", "min"):
+        w = opool.segment_csr(feat, ref["indices"], ref["idx_ptr"], red)
+        gg = ops.segment_reduce(dev(feat), dev(order[0]), out["seg_start"], red)
+        np.testing.assert_allclose(gg.cpu().numpy(), w, rtol=1e-5, atol=1e-5)
+    # unpool gather-add
+    child = rng.normal(size=(out["m"], 64)).astype(np.float32)
+    u, _ = ops.unpool_gather_add(dev(feat), dev(child), out["cluster"])
+    np.testing.assert_allclose(u.cpu().numpy(), opool.unpool_gather_add(feat, child, ref["cluster"]), rtol=1e-6)
+
+
+def test_pool_golden(golden):
+    from scenesplat_b200 import ops
+    g = golden("pooling.npz")
+    offset = g["offset"]
+    perms = g["perms"]
+    depth = ops.coord_depth(dev(g["grid_coord"]))
+    b, code, order, inv = ops.serialize(dev(g["grid_coord"]), dev(offset), depth, [ORDERS[i] for i in perms[0]])
+    np.testing.assert_array_equal(code.cpu().numpy(), g["parent_code"])
+    out = ops.pool_index(code, order, dev(g["grid_coord"]), b, 1, list(perms[1]))
+    np.testing.assert_array_equal(out["cluster"].cpu().numpy(), g["cluster"])
+    np.testing.assert_array_equal(out["code"].cpu().numpy(), g["code"])
+    np.testing.assert_array_equal(out["order"].cpu().numpy(), g["order"])
+    np.testing.assert_array_equal(out["inverse"].cpu().numpy(), g["inverse"])
+    np.testing.assert_array_equal(out["grid_coord"].cpu().numpy(), g["out_grid_coord"])
+    np.testing.assert_array_equal(out["batch"].cpu().numpy(), g["out_batch"])
+    # fused mean -> BN(eval) -> GELU epilogue against the reference module's output
+    sd = {k[3:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith("sd.")}
+    proj = torch.nn.functional.linear(dev(g["feat"]), sd["proj.weight"], sd["proj.bias"])
+    scale = sd["norm.0.weight"] / torch.sqrt(sd["norm.0.running_var"] + 1e-3)
+    shift = sd["norm.0.bias"] - sd["norm.0.running_mean"] * scale
+    feat = ops.segment_reduce(proj, order[0].contiguous(), out["seg_start"], "mean", scale.contiguous(),
+                              shift.contiguous(), act=1)
+    np.testing.assert_allclose(feat.cpu().numpy(), g["out_feat"], rtol=2e-4, atol=2e-5)
+    coord = ops.segment_reduce(dev(g["coord"]), order[0].contiguous(), out["seg_start"], "mean")
+    np.testing.assert_allclose(coord.cpu().numpy(), g["out_coord"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("k,row", [(3, 0), (3, 2), (5, 1), (3, 3)])
+def test_kernel_map_vs_oracle(k, row):
+    from scenesplat_b200 import ops
+    _, g, offset = _parent(20000, seed=6)
+    batch = oser.offset2batch(offset)
+    code, order, inv, depth = oser.serialization(g, batch, len(offset), ORDERS)
+    nbr, cnt = ops.kmap_build(dev(g), dev(batch), dev(code[row]), dev(order[row]), depth, row, k)
+    ref = oconv.kernel_map(g, batch, k)
+    np.testing.assert_array_equal(nbr.cpu().numpy().T, ref)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), (ref >= 0).sum(0))
+    pairs = ops.kmap_pairs(nbr, dev(order[row]), k, cnt.cpu().numpy())
+    ypos = pairs["ypos"].cpu().numpy().T  # [n, k3]
+    pin = pairs["pair_in"].cpu().numpy()
+    assert ((ypos >= 0) == (ref >= 0)).all()
+    sel = ref >= 0
+    np.testing.assert_array_equal(pin[ypos[sel]], ref[sel])
+    assert np.unique(ypos[sel]).size == sel.sum()
+    assert pairs["p_pad"] % 128 == 0
+
+
+def test_patch_table_vs_golden(golden):
+    from scenesplat_b200 import ops
+    g = golden("patch_table.npz")
+    for i in range(int(g["n_cases"])):
+        offset, K = g[f"c{i}_offset"], int(g[f"c{i}_K"])
+        n = int(offset[-1])
+        table = ops.patch_table(dev(offset), K, n).cpu().numpy()
+        pad, unpad, cu = g[f"c{i}_pad"], g[f"c{i}_unpad"], g[f"c{i}_cu"]
+        # rebuild pad / unpad / cu_seqlens from the table and compare with the reference's arrays
+        rows = [t for t in table if t[1] > t[0]]
+        assert len(rows) == len(cu) - 1
+        seq_pad, seq_unpad = [], np.zeros(n, dtype=np.int64)
+        pos = 0
+        for qb, qe, kb, ke in rows:
+            own = list(range(qb, qe))
+            borrowed = [j for j in range(kb, ke) if j < qb]
+            for t, j in enumerate(own):
+                seq_unpad[j] = pos + t
+            seq_pad += own + borrowed
+            pos += (ke - kb)
+        np.testing.assert_array_equal(np.array(seq_pad), pad)
+        np.testing.assert_array_equal(seq_unpad, unpad)
+        np.testing.assert_array_equal(np.cumsum([0] + [r[3] - r[2] for r in rows]), cu)
