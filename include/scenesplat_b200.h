@@ -187,8 +187,9 @@ int ss_class_half_sums(const void* pred, int pred_is_bf16, const uint8_t* mask, 
                        const int64_t* half, int64_t n, int channels, int n_classes, float* sums, int32_t* counts,
                        void* stream);
 
-/* Library / build identification. */
+/* Library / build identification; number of kernels this library has launched in the process. */
 const char* ss_version(void);
+uint64_t ss_launch_count(void);
 
 #ifdef __cplusplus
 }

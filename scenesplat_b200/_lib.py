@@ -45,6 +45,7 @@ SIGNATURES = {
     "ss_cos_l2_loss": (_i, [_vp, _i, _vp, _i, _vp, _i64, _i, _vp, _vp]),
     "ss_class_half_sums": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "ss_version": (C.c_char_p, []),
+    "ss_launch_count": (C.c_uint64, []),
 }
 
 _lib = None
@@ -97,10 +98,25 @@ def int_array(vals):
     return (C.c_int * len(vals))(*[int(v) for v in vals])
 
 
-def call(name: str, *args):
+# Optional per-call device timing (bench.py): name -> list of (start_event, end_event, meta)
+PROFILE = None
+
+
+def call(name: str, *args, meta=None):
     lib = load()
+    if PROFILE is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     rc = getattr(lib, name)(*args)
+    e1.record()
     check(rc, name)
+    PROFILE.setdefault(name, []).append((e0, e1, meta))
+
+
+def launch_count() -> int:
+    return int(load().ss_launch_count())
 
 
 def workspace(nbytes: int, device):

@@ -7,8 +7,11 @@
 #define SS_OK 0
 #define SS_BAD_ARGS (-1)
 
+// Every kernel launch site is followed by SS_CHECK_LAUNCH(): it also counts the launch (ss_launch_count()).
+namespace ss { extern unsigned long long g_launch_count; }
 #define SS_CHECK_LAUNCH()                         \
   do {                                            \
+    ++ss::g_launch_count;                         \
     cudaError_t e__ = cudaGetLastError();         \
     if (e__ != cudaSuccess) return (int)e__;      \
   } while (0)

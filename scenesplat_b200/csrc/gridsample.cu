@@ -178,6 +178,7 @@ int ss_gridsample_index(const float* coord, int64_t n, double grid_size, int has
   uint64_t* key_sorted = (uint64_t*)(ws + p.off_keysorted);
   SS_CUDA(cudaMemsetAsync(ws + p.radix.off_hist, 0, p.radix.zero_bytes, stream));
   ss::gs_init_minmax<<<1, 32, 0, stream>>>(mn, mx);
+  SS_CHECK_LAUNCH();
   const int blocks = (int)ss::imin64(ss::ceil_div64(n, 256), 8 * ss::kNumSMs);
   ss::gs_minmax_kernel<<<blocks, 256, 0, stream>>>(coord, n, grid_size, mn, mx);
   SS_CHECK_LAUNCH();

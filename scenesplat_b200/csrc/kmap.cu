@@ -123,6 +123,7 @@ int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* bat
   uint64_t* skeys = (uint64_t*)ws;
   const int blocks = ss::ceil_div((int)n, 256);
   ss::sorted_keys_kernel<<<min(blocks, 16 * ss::kNumSMs), 256, 0, stream>>>(code_row, order_row, n, skeys);
+  SS_CHECK_LAUNCH();
   // mirrored half (taps > centre) is only written where a neighbour exists
   SS_CUDA(cudaMemsetAsync(nbr + (size_t)(k3 / 2 + 1) * n, 0xff, (size_t)(k3 / 2) * n * 4, stream));
   const size_t smem = (size_t)(k3 / 2) * 4;

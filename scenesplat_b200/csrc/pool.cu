@@ -202,6 +202,7 @@ int ss_pool_index(const int64_t* code, const int64_t* order, const int64_t* grid
   int rc = ss::runs_launch(f0, n, ws, m_dev, stream, 1);
   if (rc) return rc;
   ss::pool_close_start<<<1, 32, 0, stream>>>(seg_start, m_dev, n);
+  SS_CHECK_LAUNCH();
   ss::PoolRowsN fn;
   fn.code = code; fn.order = order; fn.cluster = cluster; fn.n = n; fn.shift = 3 * pooling_depth; fn.m_cap = m_cap;
   fn.corder = child_order; fn.cinverse = child_inverse;

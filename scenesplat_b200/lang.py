@@ -1,0 +1,180 @@
+"""Language-pretraining wrapper, losses and zero-shot head on the sm_100a kernels.
+
+Drop-in for (reference):
+  LangPretrainer                 pointcept/models/default.py:77-176
+  Criteria / build_criteria      pointcept/models/losses/builder.py:13-36
+  CosineSimilarity, L2Loss, AggregatedContrastiveLoss   pointcept/models/losses/misc.py:247-421
+  zero-shot head                 pointcept/engines/hooks/evaluator.py:793-800, pointcept/engines/test.py:335-349
+Forward values only (no autograd through the fused kernels yet).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .registry import LOSSES, MODELS, build_model
+from .structure import Point
+
+
+@LOSSES.register_module()
+class CosineSimilarity(nn.Module):
+    def __init__(self, reduction="mean", loss_weight=1.0):
+        super().__init__()
+        self.reduction, self.loss_weight = reduction, loss_weight
+
+    def forward(self, pred, target, valid_feat_mask, **kwargs):
+        acc = ops.cos_l2_sums(pred, target, valid_feat_mask)
+        loss = acc[0]
+        if self.reduction == "mean":
+            loss = torch.where(acc[2] > 0, acc[0] / acc[2].clamp(min=1), acc[0])
+        return self.loss_weight * loss.float()
+
+
+@LOSSES.register_module()
+class L2Loss(nn.Module):
+    def __init__(self, reduction="mean", loss_weight=1.0):
+        super().__init__()
+        self.reduction, self.loss_weight = reduction, loss_weight
+
+    def forward(self, pred, target, valid_feat_mask, **kwargs):
+        acc = ops.cos_l2_sums(pred, target, valid_feat_mask)
+        loss = acc[1]
+        if self.reduction == "mean":
+            loss = torch.where(acc[2] > 0, acc[1] / acc[2].clamp(min=1), acc[1])
+        return self.loss_weight * loss.float()
+
+
+@LOSSES.register_module()
+class AggregatedContrastiveLoss(nn.Module):
+    def __init__(self, temperature=0.2, reduction="mean", loss_weight=1.0, schedule="all", max_classes=256):
+        super().__init__()
+        self.temperature, self.reduction, self.loss_weight, self.schedule = temperature, reduction, loss_weight, schedule
+        self.max_classes = max_classes
+        if "last_" in self.schedule:
+            self.last_percent = float(self.schedule.split("_")[-1]) / 100
+
+    @staticmethod
+    def random_halves(valid, segment, n_classes):
+        """Per-class random half split, one device pass (the reference loops over labels with a
+        `torch.randperm` each, losses/misc.py:361-372): rank points inside their class by a random key;
+        the first n//2 of each class form group a (0), the rest group b (1)."""
+        n = segment.shape[0]
+        lab = torch.where(valid, segment.long(), torch.full_like(segment.long(), n_classes))
+        key = lab.double() + torch.rand(n, device=segment.device, dtype=torch.float64) * 0.5
+        order = torch.argsort(key)
+        counts = torch.bincount(lab, minlength=n_classes + 1)
+        start = torch.cumsum(counts, 0) - counts
+        rank = torch.empty(n, dtype=torch.long, device=segment.device)
+        rank[order] = torch.arange(n, device=segment.device) - start[lab[order]]
+        return (rank >= counts[lab] // 2).long(), counts[:n_classes]
+
+    def forward(self, pred, target, valid_feat_mask, segment, epoch_progress=None, half=None, **kwargs):
+        device = pred.device
+        if "last_" in self.schedule and epoch_progress is not None:
+            if epoch_progress <= (1 - self.last_percent):
+                return torch.tensor(0.0, device=device)
+        elif self.schedule == "skip":
+            return torch.tensor(0.0, device=device)
+        if segment is None:
+            return torch.tensor(0.0, device=device)
+        valid = (valid_feat_mask > 0) & (segment != -1)
+        nc = self.max_classes
+        if half is None:
+            half, _ = self.random_halves(valid, segment, nc)
+        sums, counts = ops.class_half_sums(pred, valid, segment, half, nc)
+        per_class = counts.view(nc, 2).sum(1)
+        use = (per_class >= 100) & (counts.view(nc, 2).min(1).values > 0)  # losses/misc.py:366-376
+        idx = use.nonzero(as_tuple=True)[0]
+        if idx.numel() == 0:
+            return torch.tensor(0.0, device=device)
+        s = sums.view(nc, 2, -1)[idx]
+        a = F.normalize(s[:, 0], p=2, dim=1)
+        b = F.normalize(s[:, 1], p=2, dim=1)
+        logits = a @ b.t() / self.temperature
+        tgt = torch.arange(logits.shape[0], device=device)
+        loss = (F.cross_entropy(logits, tgt) + F.cross_entropy(logits.t(), tgt)) / 2.0
+        if self.reduction == "sum":
+            loss = loss * logits.shape[0]
+        return self.loss_weight * loss
+
+
+class Criteria(object):
+    """losses/builder.py:13-32"""
+
+    def __init__(self, cfg=None):
+        self.cfg = cfg if cfg is not None else []
+        self.criteria = [LOSSES.build(cfg=c) for c in self.cfg]
+
+    def __call__(self, pred, target, **kwargs):
+        if len(self.criteria) == 0:
+            return pred
+        loss = 0
+        for c in self.criteria:
+            loss = loss + c(pred, target, **kwargs)
+        return loss
+
+
+def build_criteria(cfg):
+    return Criteria(cfg)
+
+
+@MODELS.register_module()
+class LangPretrainer(nn.Module):
+    """default.py:77-176"""
+
+    def __init__(self, backbone=None, criteria=None):
+        super().__init__()
+        self.backbone = build_model(backbone)
+        self.criteria = build_criteria(criteria)
+
+    def _features(self, input_dict):
+        point = Point(input_dict)
+        point_feat = self.backbone(point)
+        point_feat["feat"] = ops.l2_normalize(point_feat["feat"], eps=1e-12)  # F.normalize(p=2, dim=1), default.py:98
+        return point_feat
+
+    def forward(self, input_dict, chunk_size=None):
+        if chunk_size is not None and chunk_size > 0 and input_dict["coord"].shape[0] > chunk_size:
+            return self._chunked_forward(input_dict, chunk_size)
+        point_feat = self._features(input_dict)
+        if self.training:
+            segment = input_dict["segment"] if "segment" in input_dict.keys() else None
+            loss = self.criteria(point_feat["feat"], input_dict["lang_feat"],
+                                 valid_feat_mask=input_dict["valid_feat_mask"], segment=segment,
+                                 epoch_progress=input_dict["epoch_progress"])
+            return dict(loss=loss)
+        return dict(point_feat=point_feat)
+
+    def _chunked_forward(self, input_dict, chunk_size):
+        """default.py:115-176: contiguous index-range chunks, independent backbone passes."""
+        coords = input_dict["coord"]
+        N = coords.shape[0]
+        outs = []
+        for start in range(0, N, chunk_size):
+            end = min(start + chunk_size, N)
+            chunk = {k: v[start:end] for k, v in input_dict.items() if isinstance(v, torch.Tensor) and v.shape[0] == N}
+            if "condition" in input_dict.keys():
+                chunk["condition"] = input_dict["condition"][0]
+            chunk["offset"] = torch.tensor([end - start], device=coords.device)
+            pf = self._features(chunk)
+            if self.training:
+                outs.append(self.criteria(pf["feat"], chunk["lang_feat"], valid_feat_mask=chunk["valid_feat_mask"],
+                                          segment=chunk.get("segment", None),
+                                          epoch_progress=chunk.get("epoch_progress", None)))
+            else:
+                outs.append(pf["feat"])
+        if self.training:
+            return dict(loss=torch.stack(outs).mean())
+        return dict(point_feat={"feat": torch.cat(outs, dim=0)})
+
+
+def zero_shot_labels(feat, text_embeddings, threshold=0.1, normalize=False):
+    """evaluator.py:793-800: sigmoid(feat @ T^T) -> (max prob, argmax label, -1 below threshold); fused."""
+    return ops.lang_head_argmax(feat, text_embeddings, normalize=normalize, threshold=threshold)
+
+
+def zero_shot_accumulate(pred_probs, feat, text_embeddings, idx_part=None):
+    """test.py:335-349: pred[idx_part] += sigmoid(feat @ T^T); fused, logits never materialised."""
+    return ops.lang_head_accumulate(feat, text_embeddings, pred_probs, idx_part)

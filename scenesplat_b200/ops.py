@@ -51,7 +51,8 @@ def serialize(grid_coord, offset, depth: int, orders, want_batch=True):
     wsb = L.load().ss_serialize_workspace_bytes(n, k, depth, nb)
     ws = L.workspace(wsb, dev)
     L.call("ss_serialize", L.ptr(g), int(g.dtype == torch.int32), L.ptr(offset), nb, n, depth, k, ids, L.ptr(batch),
-           L.ptr(code), L.ptr(order), L.ptr(inverse), L.ptr(ws), ws.numel(), L.stream())
+           L.ptr(code), L.ptr(order), L.ptr(inverse), L.ptr(ws), ws.numel(), L.stream(),
+           meta=dict(bytes=n * ((12 if g.dtype == torch.int32 else 24) + 8 + 24 * k)))
     return batch, code, order, inverse
 
 
@@ -131,7 +132,8 @@ def segment_reduce(src, order_row, seg_start, reduce="mean", scale=None, shift=N
     c = src.shape[1]
     out = torch.empty((m, c), dtype=out_dtype or src.dtype, device=src.device)
     L.call("ss_segment_reduce", L.ptr(src), _isbf(src), L.ptr(order_row), L.ptr(seg_start), None, m, c,
-           _REDUCE[reduce], L.ptr(scale), L.ptr(shift), act, L.ptr(out), _isbf(out), L.stream())
+           _REDUCE[reduce], L.ptr(scale), L.ptr(shift), act, L.ptr(out), _isbf(out), L.stream(),
+           meta=dict(bytes=src.shape[0] * (8.0 + c * src.element_size()) + m * (8.0 + c * out.element_size())))
     return out
 
 
@@ -203,10 +205,11 @@ def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16
     p_pad = pairs["p_pad"]
     prod = torch.empty((max(p_pad, 1), cout), dtype=_BF16, device=x_bf16.device)
     L.call("ss_subm_conv_gemm", L.ptr(x_bf16.contiguous()), L.ptr(pairs["pair_in"]), L.ptr(w_bf16),
-           L.ptr(pairs["tile_tap"]), p_pad, k3, cin, cout, L.ptr(prod), L.stream())
+           L.ptr(pairs["tile_tap"]), p_pad, k3, cin, cout, L.ptr(prod), L.stream(),
+           meta=dict(flops=2.0 * pairs["pairs"] * cin * cout, bytes=2.0 * pairs["pairs"] * (cin + cout)))
     out = torch.empty((n, cout), dtype=out_dtype, device=x_bf16.device)
     L.call("ss_subm_conv_reduce", L.ptr(prod), L.ptr(pairs["ypos"]), L.ptr(bias), n, k3, cout, L.ptr(out), _isbf(out),
-           L.stream())
+           L.stream(), meta=dict(bytes=2.0 * pairs["pairs"] * cout + n * (4.0 * k3 + out.element_size() * cout)))
     return out
 
 
@@ -230,12 +233,13 @@ def patch_attention(qkv, order_row, table, patch_size: int, heads: int, scale: f
              and patch_size <= 1024)
     if impl == "tc" and not tc_ok:
         raise L.CudaKernelError("tcgen05 attention needs bf16, head_dim in {16,32,48,64}, patch multiple of 128")
+    meta = dict(flops=4.0 * min(patch_size, n) * c * n, bytes=n * (4.0 * c * qkv.element_size() + 8))
     if impl == "tc":
         L.call("ss_patch_attention", L.ptr(qkv), L.ptr(order_row), L.ptr(table), table.shape[0], patch_size, heads, d,
-               float(scale), L.ptr(out), L.stream())
+               float(scale), L.ptr(out), L.stream(), meta=meta)
     else:
         L.call("ss_patch_attention_simt", L.ptr(qkv), _isbf(qkv), L.ptr(order_row), L.ptr(table), table.shape[0],
-               patch_size, heads, d, float(scale), L.ptr(out), _isbf(out), L.stream())
+               patch_size, heads, d, float(scale), L.ptr(out), _isbf(out), L.stream(), meta=meta)
     return out
 
 
@@ -251,9 +255,11 @@ def add_layernorm(res, delta, ln0=None, ln1=None, eps=1e-5, want_res=True, norm_
     norm_out = torch.empty((n, c), dtype=norm_dtype, device=dev) if norm_dtype is not None else None
     g0, b0 = ln0 if ln0 is not None else (None, None)
     g1, b1 = ln1 if ln1 is not None else (None, None)
+    nbytes = n * c * ((4 if res is not None else 0) + (delta.element_size() if delta is not None else 0)
+                      + (4 if res_out is not None else 0) + (norm_out.element_size() if norm_out is not None else 0))
     L.call("ss_add_layernorm", L.ptr(res), L.ptr(delta), _isbf(delta) if delta is not None else 0, L.ptr(g0), L.ptr(b0),
            L.ptr(g1), L.ptr(b1), float(eps), n, c, L.ptr(res_out), L.ptr(norm_out),
-           _isbf(norm_out) if norm_out is not None else 0, L.stream())
+           _isbf(norm_out) if norm_out is not None else 0, L.stream(), meta=dict(bytes=float(nbytes)))
     return res_out, norm_out
 
 

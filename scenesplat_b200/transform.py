@@ -1,0 +1,92 @@
+"""GridSample on the GPU -- drop-in for pointcept/datasets/transform.py:1181-1416 (same constructor
+kwargs and dict keys).  The voxel hash / sort / unique / select run as sm_100a kernels; attribute
+arrays are gathered on the device.  Accepts numpy arrays (returned as numpy, like the reference) or
+torch tensors (returned on the GPU, which skips the host round trip when the model follows directly).
+
+Deterministic outputs are bit-exact with the reference (`inverse`, `grid_coord`, voxel order, counts).
+The representative of a voxel is member `r % count` of the voxel's members in ORIGINAL INDEX order,
+with `r` drawn from numpy's global RNG exactly like transform.py:1264-1267 (the reference's own
+choice additionally depends on numpy's unstable introsort, so only membership can be compared).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .registry import TRANSFORMS
+
+
+@TRANSFORMS.register_module()
+class GridSample(object):
+    def __init__(self, grid_size=0.05, hash_type="fnv", mode="train", keys=("coord", "color", "normal", "segment"),
+                 return_inverse=False, return_grid_coord=False, return_min_coord=False, return_displacement=False,
+                 project_displacement=False, importance_sample_key=None, apply_to_pc=True, device="cuda"):
+        assert mode in ["train", "test"]
+        if importance_sample_key is not None:
+            raise NotImplementedError("importance sampling is not used by the lang configs (out of scope)")
+        self.grid_size, self.hash_type, self.mode, self.keys = grid_size, hash_type, mode, keys
+        self.return_inverse, self.return_grid_coord = return_inverse, return_grid_coord
+        self.return_min_coord, self.return_displacement = return_min_coord, return_displacement
+        self.project_displacement, self.apply_to_pc = project_displacement, apply_to_pc
+        self.device = device
+
+    def _to_dev(self, v):
+        if isinstance(v, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(v)).to(self.device, non_blocking=True)
+        return v.to(self.device, non_blocking=True)
+
+    def __call__(self, data_dict):
+        assert "coord" in data_dict.keys()
+        if "pc_coord" in data_dict and self.apply_to_pc:
+            raise NotImplementedError("pc_coord co-sampling is dataset-specific preprocessing (out of scope)")
+        if "sampled_index" in data_dict:
+            raise NotImplementedError("sampled_index (ScanNet data-efficient) is out of scope")
+        as_numpy = isinstance(data_dict["coord"], np.ndarray)
+        coord = self._to_dev(data_dict["coord"]).float().contiguous()
+        ix = ops.gridsample_index(coord, self.grid_size, self.hash_type)
+        m = ix["m"]
+        count = ix["start"][1: m + 1] - ix["start"][:m]
+        back = (lambda t: t.cpu().numpy()) if as_numpy else (lambda t: t)
+
+        def emit(idx, gc, out):
+            if self.return_grid_coord:
+                out["grid_coord"] = back(gc)
+            if self.return_min_coord:
+                mn = ix["min_coord"].double() * self.grid_size
+                out["min_coord"] = back(mn.reshape(1, 3))
+            if self.return_displacement:
+                scaled = coord[idx].double() / self.grid_size - ix["min_coord"].double()
+                disp = scaled - gc.double() - 0.5
+                if self.project_displacement:
+                    disp = (disp * self._to_dev(data_dict["normal"])[idx]).sum(-1, keepdim=True)
+                out["displacement"] = back(disp)
+
+        if self.mode == "train":
+            cmax = int(count.max()) if m > 0 else 1
+            rnd = torch.from_numpy(np.random.randint(0, cmax, m)).to(self.device)
+            idx, gc, _ = ops.gridsample_select(ix, rnd, want_grid_coord=True)
+            if self.return_inverse:
+                data_dict["inverse"] = back(ix["inverse"])
+            emit(idx, gc, data_dict)
+            for key in self.keys:
+                if key in data_dict.keys():
+                    data_dict[key] = back(ops.gather_rows(self._to_dev(data_dict[key]), idx))
+            return data_dict
+
+        parts = []
+        cmax = int(count.max()) if m > 0 else 0
+        dev_cache = {k: self._to_dev(v) for k, v in data_dict.items() if k in self.keys}
+        for i in range(cmax):
+            idx, gc, _ = ops.gridsample_select(ix, None, frag=i, want_grid_coord=True)
+            part = dict(index=back(idx))
+            if self.return_inverse:
+                data_dict["inverse"] = back(ix["inverse"])
+            emit(idx, gc, part)
+            for key in data_dict.keys():
+                if key in self.keys:
+                    part[key] = back(ops.gather_rows(dev_cache[key], idx))
+                else:
+                    part[key] = data_dict[key]
+            parts.append(part)
+        return parts
