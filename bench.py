@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Gaussians/s through the SceneSplat lang-pretrain PTv3 encoder forward
+(BASELINE.json configs[1]: bf16, one synthetic ScanNet-sized chunk of ~300k Gaussians, patch 1024).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one forward of the full PT-v3m1 lang backbone (91.7M params, random init, eval) over one
+chunk.  N > 1 (launched by torchrun, one rank per GPU): every rank runs its own chunk (chunks are
+independent backbone passes -> no data-path collective, weak scaling); the value is all ranks'
+Gaussians / the max-over-ranks device time.
+
+JSON keys (one line, rank 0): see the harness contract.  `value` = device-resident throughput,
+`e2e` = the same forward driven through the public API (LangPretrainer + zero-shot head) from PINNED
+HOST buffers with the H2D copy of the inputs and the D2H read of the labels inside the timed region,
+`roofline` = the dominant own kernel timed with CUDA events inside the timed region,
+`cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LANG_BACKBONE = dict(
+    type="PT-v3m1", in_channels=11, order=("z", "z-trans", "hilbert", "hilbert-trans"), stride=(2, 2, 2),
+    enc_depths=(2, 2, 2, 6), enc_channels=(32, 64, 128, 256), enc_num_head=(2, 4, 8, 16),
+    enc_patch_size=(1024, 1024, 1024, 1024), dec_depths=(2, 2, 2), dec_channels=(768, 512, 256),
+    dec_num_head=(16, 16, 16), dec_patch_size=(1024, 1024, 1024), mlp_ratio=4, qkv_bias=True, qk_scale=None,
+    attn_drop=0.0, proj_drop=0.0, drop_path=0.3, shuffle_orders=True, pre_norm=True, enable_rpe=False,
+    enable_flash=True, upcast_attention=False, upcast_softmax=False, cls_mode=False,
+)
+N_RAW = 360000          # -> 299,277 voxels after GridSample(0.02) on the synthetic room (seed 0)
+CPU_SAMPLE_RAW = 14000  # bounded CPU sample: a ~12k-voxel sub-chunk of the same generator
+METRIC = "gaussians_per_s_ptv3_fwd"
+UNIT = "Gaussians/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.stop_flag, self.proc = gpu_index, [], False, None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return dict(sm_mhz=int(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def make_chunk(seed, n_raw=N_RAW):
+    from scenesplat_b200 import synthetic
+    d = synthetic.chunk(n_raw, seed=seed)
+    return d
+
+
+def build_model():
+    import scenesplat_b200 as S
+    torch.manual_seed(0)
+    model = S.LangPretrainer(backbone=dict(LANG_BACKBONE), criteria=[])
+    return model.eval()
+
+
+def voxelize_on_gpu(d, dev):
+    """GridSample(0.02) with the product's own kernels; returns host (pinned) + device input dicts."""
+    import scenesplat_b200 as S
+    gs = S.GridSample(grid_size=0.02, hash_type="fnv", mode="train", keys=("coord", "color", "opacity", "quat", "scale"),
+                      return_grid_coord=True, device=dev)
+    np.random.seed(0)
+    out = gs({k: torch.from_numpy(v) for k, v in d.items() if k in ("coord", "color", "opacity", "quat", "scale")})
+    feat = torch.cat([out["color"], out["opacity"], out["quat"], out["scale"]], 1).contiguous()
+    n = out["coord"].shape[0]
+    dev_in = dict(coord=out["coord"].contiguous(), grid_coord=out["grid_coord"].contiguous(), feat=feat,
+                  offset=torch.tensor([n], device=dev))
+    host_in = {k: v.cpu().pin_memory() for k, v in dev_in.items()}
+    return dev_in, host_in, n
+
+
+def cpu_oracle_throughput(threads=None):
+    """The CPU restatement of the reference forward (oracle/ptv3.py) on a bounded sample; Gaussians/s."""
+    from oracle import gridsample as ogs
+    from oracle import ptv3 as optv3
+    from scenesplat_b200 import synthetic
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(threads or ncpu)
+    d = synthetic.chunk(CPU_SAMPLE_RAW, L=2.4, H=1.6, seed=0)
+    res = ogs.grid_sample_train(d["coord"], 0.02)
+    idx = res["idx_unique"]
+    feat = synthetic.feat_from({k: v[idx] for k, v in d.items()})
+    n = idx.shape[0]
+    cfg = {k: v for k, v in LANG_BACKBONE.items() if k != "type"}
+    model = build_model()
+    sd = {k[len("backbone."):]: v for k, v in model.state_dict().items()}
+    perms = [np.arange(4)] * 4
+    t0 = time.perf_counter()
+    optv3.ptv3_forward(sd, cfg, d["coord"][idx], res["grid_coord"], feat, np.array([n]), perms=perms)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    n = dt = cores = None
+    for i in range(max(1, min(args.steps, 3)) + min(args.warmup, 1)):
+        v, n, dt, cores = cpu_oracle_throughput()
+        if i >= min(args.warmup, 1):
+            vals.append(v)
+    value = float(np.mean(vals))
+    sample = f"oracle/ptv3.py full-size lang PT-v3m1 forward (fp32, torch CPU) on a {n}-voxel synthetic sub-chunk"
+    line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=len(vals),
+                warmup=min(args.warmup, 1), ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="fp32", data="synthetic",
+                config=dict(workload="SceneSplat lang-pretrain PTv3 encoder forward, synthetic ScanNet-sized chunk "
+                                     "(CPU port timed on a bounded sub-chunk of the same generator)",
+                            voxels_per_step=n, patch_size=1024),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n-raw", type=int, default=N_RAW)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    from scenesplat_b200 import _lib as L
+    import scenesplat_b200 as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback in the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(args.warmup, 3)
+
+    model = build_model().to(dev)
+    text = torch.nn.functional.normalize(torch.randn(200, 768, generator=torch.Generator().manual_seed(1)), dim=1).to(dev)
+    dev_in, host_in, n_vox = voxelize_on_gpu(make_chunk(seed=rank, n_raw=args.n_raw), dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        flush.zero_()
+        with torch.no_grad():
+            return model(dict(dev_in))["point_feat"]["feat"]
+
+    def step_e2e():
+        flush.zero_()
+        with torch.no_grad():
+            d = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+            feat = model(d)["point_feat"]["feat"]
+            mx, lab = S.zero_shot_labels(feat, text)
+            return lab.to("cpu", non_blocking=True), mx.to("cpu", non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        for _ in range(warm):
+            fn()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        L.PROFILE = {} if profile else None
+        l0 = L.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof, L.PROFILE = L.PROFILE, None
+        launches = L.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, prof, launches, clocks
+
+    ms, prof, launches, clocks = timed(step_resident, args.steps, profile=True)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+    total_vox = n_vox
+    if world > 1:
+        t = torch.tensor([n_vox], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        total_vox = float(t.item())
+    value = total_vox * args.steps / (ms * 1e-3)
+    e2e_value = total_vox * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant own kernel (device time from CUDA events recorded inside the timed region)
+    pk = peaks()
+    table = {}
+    for name, recs in (prof or {}).items():
+        tms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        table[name] = dict(ms=tms, calls=len(recs), flops=sum((m or {}).get("flops", 0.0) for _, _, m in recs),
+                           bytes=sum((m or {}).get("bytes", 0.0) for _, _, m in recs))
+    top = max(table.items(), key=lambda kv: kv[1]["ms"]) if table else (None, None)
+    roofline = None
+    if top[0] is not None:
+        name, r = top
+        if r["flops"] > 0:
+            ach = r["flops"] / (r["ms"] * 1e-3) / 1e12
+            roofline = dict(kernel=name, bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s",
+                            frac=ach / pk["tf_sust"], traffic=None, peak_source=pk["src"] + " (sustained bf16)",
+                            share_of_step=r["ms"] / ms, calls_per_step=r["calls"] / args.steps)
+        else:
+            ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+            roofline = dict(kernel=name, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
+                            traffic=None, peak_source=pk["src"], share_of_step=r["ms"] / ms,
+                            calls_per_step=r["calls"] / args.steps)
+    own_ms = sum(r["ms"] for r in table.values())
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, n, dt, cores = cpu_oracle_throughput()
+            cpu = dict(value=v, unit=UNIT, cores=cores, kind="port",
+                       sample=f"oracle/ptv3.py full-size lang PT-v3m1 forward (fp32) on a {n}-voxel synthetic sub-chunk, "
+                              f"{dt:.1f} s")
+        h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm,
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+            data="synthetic",
+            config=dict(workload="SceneSplat lang-pretrain PTv3 encoder forward (PT-v3m1 lang config, 91.7M params, "
+                                 "random init, eval), one synthetic ScanNet-sized chunk per GPU, patch 1024",
+                        voxels_per_chunk=n_vox, raw_gaussians_per_chunk=args.n_raw, grid_size=0.02,
+                        parallelism=f"chunk-sharded x{world} (no data-path collective)",
+                        l2="256 MiB flush buffer written before every step; activations (GBs) exceed L2 anyway"),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=n_vox * 12,
+                     ms_per_step=ms_e2e / args.steps,
+                     api="LangPretrainer(eval) + zero_shot_labels(K=200) from pinned host inputs"),
+            gpu_launches=launches, own_kernel_ms_per_step=own_ms / args.steps,
+            kernels={k: dict(ms_per_step=round(v["ms"] / args.steps, 4), calls_per_step=v["calls"] / args.steps)
+                     for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])},
+            roofline=roofline, cpu_baseline=cpu, clocks=clocks,
+        )
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

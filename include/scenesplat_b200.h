@@ -145,7 +145,7 @@ int ss_patch_attention_simt(const void* qkv, int in_is_bf16, const int64_t* orde
                             int max_patches, int patch_size, int heads, int head_dim, float scale, void* out,
                             int out_is_bf16, void* stream);
 
-/* tcgen05 / TMEM kernel: bf16 in/out, head_dim in {16, 32, 48, 64}, patch_size multiple of 128 (<= 1024). */
+/* tcgen05 / TMEM kernel: bf16 in/out, head_dim in {16, 32, 48}, patch_size <= 1024 (any sequence length). */
 int ss_patch_attention(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
                        int patch_size, int heads, int head_dim, float scale, void* out_bf16, void* stream);
 

@@ -163,3 +163,32 @@ def test_lang_head_and_losses_golden(golden):
     con = olang.contrastive_from_sums(torch.stack([sums[2 * l] for l in labs.tolist()]).cpu(),
                                       torch.stack([sums[2 * l + 1] for l in labs.tolist()]).cpu(), 0.2, 0.025)
     np.testing.assert_allclose(con.numpy(), g["con"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("H,d,K", [(2, 16, 1024), (3, 32, 1024), (2, 48, 1024), (4, 16, 256), (1, 48, 100)])
+def test_patch_attention_tensor_core(H, d, K):
+    """tcgen05 kernel vs the fp32 oracle AND vs the independent SIMT kernel on the same bf16 inputs.
+    Tolerance: P is rounded to bf16 before P.V (2^-9 relative per term) and the result to bf16 (2^-9):
+    2e-2 absolute on outputs of magnitude <= ~1 (convex combinations of N(0,1) values)."""
+    from scenesplat_b200 import ops
+    rng = np.random.default_rng(1)
+    offset = np.array([K // 2 + 3, K // 2 + 3 + 2 * K + 17, 4 * K + 40 + 333], dtype=np.int64)
+    n = int(offset[-1])
+    C = H * d
+    torch.manual_seed(0)
+    qkv = (torch.randn(n, 3 * C) * 1.5).bfloat16()
+    order = np.concatenate([rng.permutation(np.arange(a, b)) for a, b in zip([0, *offset[:-1]], offset)])
+    inverse = np.empty(n, dtype=np.int64)
+    inverse[order] = np.arange(n)
+    scale = d ** -0.5
+    want = oattn.serialized_attention_core(qkv.float(), order, inverse, offset, K, H, scale)
+    table = ops.patch_table(dev(offset), K, n)
+    got = ops.patch_attention(qkv.cuda(), dev(order), table, K, H, scale, impl="tc")
+    simt = ops.patch_attention(qkv.cuda(), dev(order), table, K, H, scale, impl="simt")
+    torch.cuda.synchronize()
+    err = (got.float().cpu() - want).abs().max().item()
+    err_simt = (got.float() - simt.float()).abs().max().item()
+    assert err < 2e-2, err
+    assert err_simt < 2e-2, err_simt
+    rel = ((got.float().cpu() - want).norm() / want.norm()).item()
+    assert rel < 1e-2, rel
