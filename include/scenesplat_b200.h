@@ -176,6 +176,12 @@ int ss_lang_head(const void* feat, int feat_is_bf16, const float* text, int64_t 
                  int normalize, float threshold, int mode, const int64_t* idx, float* max_prob, int64_t* label,
                  float* probs_accum, void* stream);
 
+/* Same head on the tensor cores (tcgen05 GEMM, max/argmax or accumulate fused into the TMEM epilogue):
+ * bf16 feat [n, channels] and bf16 text [n_classes <= 256, channels], fp32 accumulate. */
+int ss_lang_head_tc(const void* feat_bf16, const void* text_bf16, int64_t n, int channels, int n_classes,
+                    float threshold, int mode, const int64_t* idx, float* max_prob, int64_t* label, float* probs_accum,
+                    void* stream);
+
 /* acc3 = {sum_valid (1 - cos), sum_valid ||pred - target||^2, n_valid} as doubles
  * (pointcept/models/losses/misc.py:247-295).  target_dtype: 0 fp32, 1 bf16, 2 fp16. */
 int ss_cos_l2_loss(const void* pred, int pred_is_bf16, const void* target, int target_dtype, const uint8_t* mask,

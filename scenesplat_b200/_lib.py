@@ -42,6 +42,7 @@ SIGNATURES = {
     "ss_affine_act": (_i, [_vp, _i, _vp, _vp, _i, _i64, _i, _vp, _i, _vp]),
     "ss_l2_normalize": (_i, [_vp, _i, _i64, _i, _f, _vp, _i, _vp]),
     "ss_lang_head": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ss_lang_head_tc": (_i, [_vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "ss_cos_l2_loss": (_i, [_vp, _i, _vp, _i, _vp, _i64, _i, _vp, _vp]),
     "ss_class_half_sums": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "ss_version": (C.c_char_p, []),
@@ -98,13 +99,15 @@ def int_array(vals):
     return (C.c_int * len(vals))(*[int(v) for v in vals])
 
 
-# Optional per-call device timing (bench.py): name -> list of (start_event, end_event, meta)
+# Optional per-call device timing (bench.py): name -> list of (start_event, end_event, meta).
+# PROFILE_ONLY (a set of names) restricts the instrumentation to a few kernels so it can stay on inside a timed region.
 PROFILE = None
+PROFILE_ONLY = None
 
 
 def call(name: str, *args, meta=None):
     lib = load()
-    if PROFILE is None:
+    if PROFILE is None or (PROFILE_ONLY is not None and name not in PROFILE_ONLY):
         check(getattr(lib, name)(*args), name)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

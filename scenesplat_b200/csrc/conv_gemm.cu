@@ -30,11 +30,22 @@ struct GemmSmem {
   static constexpr int kTotal = kBarOffset + 1024 /*barriers, indices*/ + 1024 /*alignment slack*/;
 };
 
-template <int BN, int STAGES>
+// Epilogue of the language head (EPI = 1: max/argmax of sigmoid(logits); EPI = 2: probs accumulate).
+struct HeadEpi {
+  int64_t n_rows;
+  int n_classes;
+  float threshold;
+  float* max_prob;
+  int64_t* label;
+  float* probs_accum;
+  const int64_t* idx;
+};
+
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads)
 gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restrict__ pair_in,
                    const __grid_constant__ CUtensorMap tmap_w, const int32_t* __restrict__ tile_tap, int cin, int cout,
-                   __nv_bfloat16* __restrict__ prod) {
+                   __nv_bfloat16* __restrict__ prod, HeadEpi head) {
   using S = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -47,10 +58,17 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int n0 = blockIdx.y * BN;
-  const int tap = tile_tap[tile];
+  const int tap = EPI == 0 ? tile_tap[tile] : 0;
   const int nk = (cin + kBK - 1) / kBK;
 
-  if (threadIdx.x < kTileM) s_rows[threadIdx.x] = pair_in[(size_t)tile * kTileM + threadIdx.x];
+  if (threadIdx.x < kTileM) {
+    if (EPI == 0) {
+      s_rows[threadIdx.x] = pair_in[(size_t)tile * kTileM + threadIdx.x];
+    } else {  // identity rows, clamped (rows past n_rows are computed but never written)
+      const int64_t r = (int64_t)tile * kTileM + threadIdx.x;
+      s_rows[threadIdx.x] = (int32_t)(r < head.n_rows ? r : head.n_rows - 1);
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(&full_bar[s], 128 + 1);  // 128 cp.async producers + 1 TMA expect_tx arrive
@@ -90,8 +108,40 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
     tc::mbar_wait(accum_bar, 0);
     tc::tc_fence_after();
     const int row = warp * 32 + lane;
-    __nv_bfloat16* orow = prod + ((size_t)tile * kTileM + row) * cout + n0;
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if constexpr (EPI != 0) {
+      const int64_t grow = (int64_t)tile * kTileM + row;
+      float best = -INFINITY;
+      int arg = 0;
+      float* prow = nullptr;
+      if (EPI == 2 && grow < head.n_rows)
+        prow = head.probs_accum + (size_t)(head.idx ? head.idx[grow] : grow) * head.n_classes;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        if (j * 32 >= head.n_classes) break;
+        uint32_t v[32];
+        tc::tmem_ld32(t_lane + j * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const int k = j * 32 + u;
+          const float lg = __uint_as_float(v[u]);
+          if (k < head.n_classes) {
+            if (EPI == 1) {
+              if (lg > best) { best = lg; arg = k; }
+            } else if (prow) {
+              prow[k] += 1.f / (1.f + __expf(-lg));
+            }
+          }
+        }
+      }
+      if (EPI == 1 && grow < head.n_rows) {
+        const float pr = 1.f / (1.f + __expf(-best));
+        head.max_prob[grow] = pr;
+        head.label[grow] = pr < head.threshold ? -1 : arg;
+      }
+    } else {
+    __nv_bfloat16* orow = prod + ((size_t)tile * kTileM + row) * cout + n0;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       if (n0 + j * 32 >= cout) break;
@@ -108,6 +158,7 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
         o.w = tc::pack_bf16(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7]));
         dst[u] = o;
       }
+    }
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ B producer (TMA, one lane)
@@ -194,11 +245,24 @@ template <int BN, int STAGES>
 static int launch_gather_gemm(const void* X, const int32_t* pair_in, const CUtensorMap& tmap, const int32_t* tile_tap,
                               int64_t tiles, int cin, int cout, void* prod, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES>;
-  auto kern = gather_gemm_kernel<BN, STAGES>;
+  auto kern = gather_gemm_kernel<BN, STAGES, 0>;
   SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   dim3 grid((unsigned)tiles, (unsigned)((cout + BN - 1) / BN));
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>((const __nv_bfloat16*)X, pair_in, tmap, tile_tap, cin, cout,
-                                                  (__nv_bfloat16*)prod);
+                                                  (__nv_bfloat16*)prod, HeadEpi{});
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+template <int EPI>
+static int launch_head(const void* feat, const CUtensorMap& tmap, int64_t n, int channels, const HeadEpi& head,
+                       cudaStream_t stream) {
+  using S = GemmSmem<256, 2>;
+  auto kern = gather_gemm_kernel<256, 2, EPI>;
+  SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  dim3 grid((unsigned)ceil_div64(n, kTileM), 1);
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>((const __nv_bfloat16*)feat, nullptr, tmap, nullptr, channels, 256,
+                                                  nullptr, head);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
@@ -206,6 +270,24 @@ static int launch_gather_gemm(const void* X, const int32_t* pair_in, const CUten
 }  // namespace ss
 
 extern "C" {
+
+int ss_lang_head_tc(const void* feat_bf16, const void* text_bf16, int64_t n, int channels, int n_classes,
+                    float threshold, int mode, const int64_t* idx, float* max_prob, int64_t* label, float* probs_accum,
+                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || channels < 16 || channels % 16 != 0 || n_classes < 1 || n_classes > 256 || (mode != 0 && mode != 1))
+    return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if (!feat_bf16 || !text_bf16 || ((uintptr_t)feat_bf16 | (uintptr_t)text_bf16) % 16 != 0) return SS_BAD_ARGS;
+  if (mode == 0 && (!max_prob || !label)) return SS_BAD_ARGS;
+  if (mode == 1 && !probs_accum) return SS_BAD_ARGS;
+  CUtensorMap tmap;  // text [n_classes, channels]: rows past n_classes read as zero (TMA OOB fill)
+  int rc = ss::make_tmap_bf16_2d(&tmap, text_bf16, (uint64_t)n_classes, (uint64_t)channels, 256, ss::kBK);
+  if (rc) return rc;
+  ss::HeadEpi head{n, n_classes, threshold, max_prob, label, probs_accum, idx};
+  return mode == 0 ? ss::launch_head<1>(feat_bf16, tmap, n, channels, head, stream)
+                   : ss::launch_head<2>(feat_bf16, tmap, n, channels, head, stream);
+}
 
 int ss_subm_conv_gemm(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
                       int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream_) {

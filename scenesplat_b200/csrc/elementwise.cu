@@ -96,6 +96,148 @@ add_layernorm_kernel(const float* res, const TD* __restrict__ delta, const float
   }
 }
 
+
+// ---- vectorised variant (C % 8 == 0): TPR threads cooperate on a row, each owning NCH chunks of 8
+// contiguous channels (16-byte bf16 / 2 x 16-byte fp32 accesses).  All loads of a row are issued before
+// any store (res and res_out may alias, so the compiler must not be left to interleave them).
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float2 f = __bfloat1622float2(h[u]);
+    v[2 * u] = f.x;
+    v[2 * u + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 o;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+template <int TPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = TPR / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TD, typename TN, int TPR, int NCH>
+__global__ void __launch_bounds__(256)
+add_layernorm_vec_kernel(const float* res, const TD* __restrict__ delta, const float* __restrict__ g0,
+                         const float* __restrict__ b0, const float* __restrict__ g1, const float* __restrict__ b1,
+                         float eps, int64_t n, int C, float* res_out, TN* __restrict__ norm_out) {
+  constexpr int RPW = 32 / TPR;  // rows per warp
+  const int lane = threadIdx.x & 31, t = lane % TPR, sub = lane / TPR;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float invC = 1.f / (float)C;
+  const int nchunk = C >> 3;
+  for (int64_t r0 = warp0 * RPW; r0 < n; r0 += nwarp * RPW) {
+    const int64_t r = r0 + sub;
+    const bool rok = r < n;
+    float v[NCH][8], x[NCH][8];
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) {
+      const int c = t + TPR * u;
+      const bool ok = rok && c < nchunk;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[u][e] = x[u][e] = 0.f;
+      if (ok && delta) ld8(delta + (size_t)r * C + c * 8, v[u]);
+      if (ok && res) ld8(res + (size_t)r * C + c * 8, x[u]);
+    }
+    if (g0) {
+      float s = 0.f;
+#pragma unroll
+      for (int u = 0; u < NCH; ++u)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[u][e];
+      const float mean = group_sum<TPR>(s) * invC;
+      float q = 0.f;
+#pragma unroll
+      for (int u = 0; u < NCH; ++u) {
+        const bool ok = (t + TPR * u) < nchunk;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = ok ? v[u][e] - mean : 0.f;
+          q += d * d;
+        }
+      }
+      const float rstd = rsqrtf(group_sum<TPR>(q) * invC + eps);
+#pragma unroll
+      for (int u = 0; u < NCH; ++u) {
+        const int c = t + TPR * u;
+        if (c < nchunk) {
+          float gg[8], bb[8];
+          ld8(g0 + c * 8, gg);
+          ld8(b0 + c * 8, bb);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[u][e] = (v[u][e] - mean) * rstd * gg[e] + bb[e];
+        }
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) {
+      const int c = t + TPR * u;
+      const bool ok = rok && c < nchunk;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[u][e] += x[u][e];
+        s += v[u][e];
+      }
+      if (ok && res_out) st8(res_out + (size_t)r * C + c * 8, v[u]);
+    }
+    if (norm_out) {
+      float mean = 0.f, rstd = 1.f;
+      if (g1) {
+        mean = group_sum<TPR>(s) * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+          const bool ok = (t + TPR * u) < nchunk;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float d = ok ? v[u][e] - mean : 0.f;
+            q += d * d;
+          }
+        }
+        rstd = rsqrtf(group_sum<TPR>(q) * invC + eps);
+      }
+#pragma unroll
+      for (int u = 0; u < NCH; ++u) {
+        const int c = t + TPR * u;
+        if (rok && c < nchunk) {
+          float o[8];
+          if (g1) {
+            float gg[8], bb[8];
+            ld8(g1 + c * 8, gg);
+            ld8(b1 + c * 8, bb);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (v[u][e] - mean) * rstd * gg[e] + bb[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = v[u][e];
+          }
+          st8(norm_out + (size_t)r * C + c * 8, o);
+        }
+      }
+    }
+  }
+}
+
 // out = act(x * scale[c] + shift[c]);  act: 0 none, 1 GELU(erf).  scale/shift nullable (pure activation).
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
@@ -164,6 +306,39 @@ int ss_add_layernorm(const float* res, const void* delta, int delta_is_bf16, con
   if (n < 0 || channels < 1 || channels > 32 * ss::kMaxPerLane || (g0 && !b0) || (g1 && !b1)) return SS_BAD_ARGS;
   if (n == 0) return SS_OK;
   if ((!res && !delta) || (!res_out && !norm_out)) return SS_BAD_ARGS;
+  const bool aligned = (((uintptr_t)res | (uintptr_t)delta | (uintptr_t)res_out | (uintptr_t)norm_out | (uintptr_t)g0 |
+                         (uintptr_t)b0 | (uintptr_t)g1 | (uintptr_t)b1) % 16) == 0;
+  if (channels % 8 == 0 && aligned) {
+    const int nchunk = channels / 8;
+    int tpr = 1;
+    while (tpr < 32 && tpr < nchunk) tpr <<= 1;
+    const int nch = (nchunk + tpr - 1) / tpr;
+    const int rpw = 32 / tpr;
+    const int vblocks = (int)ss::imin64(ss::ceil_div64(n, 8 * rpw), 16 * ss::kNumSMs);
+#define SS_LNV_(TD, TN, T, N)                                                                                        \
+  ss::add_layernorm_vec_kernel<TD, TN, T, N><<<vblocks, 256, 0, stream>>>(res, (const TD*)delta, g0, b0, g1, b1, eps, \
+                                                                          n, channels, res_out, (TN*)norm_out)
+#define SS_LNV_T_(TD, TN)                                        \
+  do {                                                           \
+    if (tpr == 1) SS_LNV_(TD, TN, 1, 1);                         \
+    else if (tpr == 2) SS_LNV_(TD, TN, 2, 1);                    \
+    else if (tpr == 4) SS_LNV_(TD, TN, 4, 1);                    \
+    else if (tpr == 8) SS_LNV_(TD, TN, 8, 1);                    \
+    else if (tpr == 16) SS_LNV_(TD, TN, 16, 1);                  \
+    else if (nch == 1) SS_LNV_(TD, TN, 32, 1);                   \
+    else if (nch == 2) SS_LNV_(TD, TN, 32, 2);                   \
+    else if (nch == 3) SS_LNV_(TD, TN, 32, 3);                   \
+    else SS_LNV_(TD, TN, 32, 4);                                 \
+  } while (0)
+    if (delta_is_bf16 && norm_is_bf16) SS_LNV_T_(__nv_bfloat16, __nv_bfloat16);
+    else if (delta_is_bf16) SS_LNV_T_(__nv_bfloat16, float);
+    else if (norm_is_bf16) SS_LNV_T_(float, __nv_bfloat16);
+    else SS_LNV_T_(float, float);
+#undef SS_LNV_T_
+#undef SS_LNV_
+    SS_CHECK_LAUNCH();
+    return SS_OK;
+  }
   const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8), 32 * ss::kNumSMs);
   const int vpl = (channels + 31) / 32;
 #define SS_LN_(TD, TN, V)                                                                                         \

@@ -279,10 +279,30 @@ def l2_normalize(x, eps=1e-12, out_dtype=None):
 
 
 # ------------------------------------------------------------------------------------------- language head / losses
-def lang_head_argmax(feat, text, normalize=False, threshold=0.1):
+def _head_tc_ok(feat, text):
+    return text.shape[0] <= 256 and feat.shape[1] % 16 == 0 and feat.shape[1] >= 16
+
+
+def _head_operand(feat, normalize):
+    if normalize:
+        return l2_normalize(feat, out_dtype=_BF16)
+    return feat if feat.dtype == _BF16 else feat.to(_BF16)
+
+
+def lang_head_argmax(feat, text, normalize=False, threshold=0.1, impl="auto"):
+    """impl: "simt" = fp32 CUDA-core kernel (exact fp32 logits); "tc" = tcgen05 GEMM with the max/argmax fused
+    into the TMEM epilogue (bf16 operands, fp32 accumulate); "auto" = tensor cores when the shape allows."""
     feat = feat.contiguous()
-    text = text.contiguous().float()
     n, c = feat.shape
+    if impl == "tc" or (impl == "auto" and _head_tc_ok(feat, text)):
+        fb = _head_operand(feat, normalize)
+        tb = text.contiguous().to(_BF16)
+        mx = torch.empty(n, dtype=torch.float32, device=feat.device)
+        lab = torch.empty(n, dtype=torch.int64, device=feat.device)
+        L.call("ss_lang_head_tc", L.ptr(fb), L.ptr(tb), n, c, text.shape[0], float(threshold), 0, None, L.ptr(mx),
+               L.ptr(lab), None, L.stream(), meta=dict(flops=2.0 * n * c * text.shape[0]))
+        return mx, lab
+    text = text.contiguous().float()
     mx = torch.empty(n, dtype=torch.float32, device=feat.device)
     lab = torch.empty(n, dtype=torch.int64, device=feat.device)
     L.call("ss_lang_head", L.ptr(feat), _isbf(feat), L.ptr(text), n, c, text.shape[0], int(normalize), float(threshold),
@@ -290,10 +310,15 @@ def lang_head_argmax(feat, text, normalize=False, threshold=0.1):
     return mx, lab
 
 
-def lang_head_accumulate(feat, text, probs_accum, idx=None, normalize=False):
+def lang_head_accumulate(feat, text, probs_accum, idx=None, normalize=False, impl="auto"):
     feat = feat.contiguous()
-    text = text.contiguous().float()
     n, c = feat.shape
+    if impl == "tc" or (impl == "auto" and _head_tc_ok(feat, text)):
+        fb = _head_operand(feat, normalize)
+        L.call("ss_lang_head_tc", L.ptr(fb), L.ptr(text.contiguous().to(_BF16)), n, c, text.shape[0], 0.0, 1,
+               L.ptr(idx), None, None, L.ptr(probs_accum), L.stream(), meta=dict(flops=2.0 * n * c * text.shape[0]))
+        return probs_accum
+    text = text.contiguous().float()
     L.call("ss_lang_head", L.ptr(feat), _isbf(feat), L.ptr(text), n, c, text.shape[0], int(normalize), 0.0, 1,
            L.ptr(idx), None, None, L.ptr(probs_accum), L.stream())
     return probs_accum

@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib as L
 from . import ops
 from . import spconv_compat as spconv
 from .modules import PointModule, PointSequential
@@ -82,7 +83,14 @@ def linear_bf16(lin: nn.Linear, x):
                                lin.bias.detach().to(BF16).contiguous() if lin.bias is not None else None))
     if x.dtype != BF16:
         x = x.to(BF16)
-    return F.linear(x, w, b)
+    if L.PROFILE is None or L.PROFILE_ONLY is not None:
+        return F.linear(x, w, b)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    y = F.linear(x, w, b)
+    e1.record()
+    L.PROFILE.setdefault("torch.linear(cuBLASLt)", []).append((e0, e1, dict(flops=2.0 * x.shape[0] * w.shape[0] * w.shape[1])))
+    return y
 
 
 def ln_params(ln: nn.LayerNorm):

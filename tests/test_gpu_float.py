@@ -142,14 +142,22 @@ def test_lang_head_and_losses_golden(golden):
     seg = torch.from_numpy(g["segment"]).cuda()
     half = torch.from_numpy(g["half"]).cuda()
     text = torch.from_numpy(g["text"]).cuda()
-    mx, lab = ops.lang_head_argmax(pred, text)
+    mx, lab = ops.lang_head_argmax(pred, text, impl="simt")
     np.testing.assert_allclose(mx.cpu().numpy(), g["max_prob"], rtol=1e-5, atol=1e-6)  # fp32
     np.testing.assert_array_equal(lab.cpu().numpy(), g["argmax"])
     # accumulate variant == dense sigmoid(logits)
     acc = torch.zeros(pred.shape[0], text.shape[0], device="cuda")
-    ops.lang_head_accumulate(pred, text, acc)
+    ops.lang_head_accumulate(pred, text, acc, impl="simt")
     want = torch.sigmoid(pred @ text.t())
     np.testing.assert_allclose(acc.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    # tensor-core head: bf16 operands (pred is fp16-exact but not bf16-exact; text rounds to bf16): logits move by
+    # <= ~2^-9 * ||p|| * ||t|| = 2e-3, probs by a quarter of that -> 1e-3 absolute; labels may flip only on near ties
+    mx_tc, lab_tc = ops.lang_head_argmax(pred, text, impl="tc")
+    np.testing.assert_allclose(mx_tc.cpu().numpy(), g["max_prob"], atol=1e-3)
+    assert (lab_tc.cpu().numpy() == g["argmax"]).mean() > 0.97
+    acc_tc = torch.zeros(pred.shape[0], text.shape[0], device="cuda")
+    ops.lang_head_accumulate(pred, text, acc_tc, impl="tc")
+    np.testing.assert_allclose(acc_tc.cpu().numpy(), want.cpu().numpy(), atol=1e-3)
     for tgt in (target16, target16.float()):
         a = ops.cos_l2_sums(pred, tgt, mask).cpu().numpy()
         np.testing.assert_allclose(a[0] / a[2], g["cos"], rtol=1e-5)
