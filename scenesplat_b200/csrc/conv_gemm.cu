@@ -55,7 +55,7 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
   uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
   int32_t* s_rows = (int32_t*)(smem + S::kBarOffset + 256);  // [128] gathered input rows
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably uniform
   const int tile = blockIdx.x;
   const int n0 = blockIdx.y * BN;
   const int tap = EPI == 0 ? tile_tap[tile] : 0;
@@ -82,7 +82,7 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp < 4) {
     // ------------------------------------------------------------------ A producers (gather)
@@ -172,24 +172,26 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
       }
     }
   } else {
-    // ------------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane per op)
+    {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kTileM, BN);
+      const uint64_t d_base = tc::umma_desc_sw128(0);
+      const uint32_t s0 = tc::smem_u32(smem);
       for (int kc = 0; kc < nk; ++kc) {
         const int s = kc % STAGES, it = kc / STAGES;
         tc::mbar_wait(&full_bar[s], it & 1);
         tc::tc_fence_after();
-        const uint32_t a_addr = tc::smem_u32(smem + s * S::kStageBytes);
-        const uint32_t b_addr = a_addr + S::kABytes;
+        const uint32_t a_addr = (s0 + s * S::kStageBytes) >> 4;
+        const uint32_t b_addr = a_addr + (S::kABytes >> 4);
         const int ksteps = min(kBK, cin - kc * kBK) >> 4;
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t da = tc::umma_desc_sw128(a_addr + k * 32);
-          const uint64_t db = tc::umma_desc_sw128(b_addr + k * 32);
-          tc::umma_bf16(tmem_base, da, db, idesc, (kc | k) ? 1u : 0u);
+          const uint64_t da = d_base | (uint64_t)((a_addr + 2 * k) & 0x3fff);
+          const uint64_t db = d_base | (uint64_t)((b_addr + 2 * k) & 0x3fff);
+          tc::umma_bf16_elect(tmem_base, da, db, idesc, (kc | k) ? 1u : 0u);
         }
-        tc::umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
+        tc::umma_commit_elect(&empty_bar[s]);  // frees the stage when these MMAs have read it
       }
-      tc::umma_commit(accum_bar);
+      tc::umma_commit_elect(accum_bar);
     }
   }
   tc::tc_fence_before();

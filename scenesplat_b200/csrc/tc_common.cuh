@@ -32,10 +32,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+// expires) instead of spinning through issue slots the math warps need.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 26)) __trap();
+  if (mbar_try_wait_hint(bar, parity, 2000000u)) return;
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait_hint(bar, parity, 2000000u)) {
+    if (global_timer_ns() - t0 > 20000000000ull) __trap();  // 20 s
   }
 }
 // arrive on `bar` when all cp.async issued so far by this thread have landed (counts as one expected arrival)
@@ -129,6 +149,38 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// Warp-uniform issue variants: the WHOLE warp executes these in uniform control flow with uniform operands and
+// one lane is elected inside the asm block.  Unlike `if (lane == 0) umma(...)`, the descriptors then live in
+// uniform registers from the start (no per-MMA ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall), which matters when
+// the MMAs are small (attention: M128 x N48..128 x K16 each).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (one row per thread)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -166,6 +218,12 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// bf16 rounding of a NON-NEGATIVE finite fp32 on the integer pipe (round half up): keeps the conversion off
+// the XU pipe the exponentials need.  Returns the rounded value's bits (low 16 bits zero).
+__device__ __forceinline__ uint32_t bf16_round_bits(float x) { return (__float_as_uint(x) + 0x8000u) & 0xffff0000u; }
+__device__ __forceinline__ uint32_t pack_bf16_bits(uint32_t lo_bits, uint32_t hi_bits) {
+  return __byte_perm(lo_bits, hi_bits, 0x7632);
 }
 
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a 128B-swizzled K-major tile (rows of 128 B)
