@@ -81,18 +81,24 @@ def check(rc: int, what: str):
 
 
 def ptr(t):
-    """Device pointer of a tensor (or None -> NULL).  Tensors must be contiguous CUDA tensors."""
+    """Device pointer of a tensor (or None -> NULL) as a plain int.  Tensors must be contiguous CUDA tensors."""
     if t is None:
         return None
     if not t.is_cuda:
         raise CudaKernelError("scenesplat_b200 kernels need CUDA tensors (there is no CPU fallback)")
     if not t.is_contiguous():
         raise CudaKernelError("scenesplat_b200 kernels need contiguous tensors")
-    return C.c_void_p(t.data_ptr())
+    return t.data_ptr()
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream (raw handle; ~0.3 us instead of ~20 us for current_stream())."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 def int_array(vals):
@@ -105,14 +111,21 @@ PROFILE = None
 PROFILE_ONLY = None
 
 
+_fn_cache = {}
+
+
 def call(name: str, *args, meta=None):
-    lib = load()
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
     if PROFILE is None or (PROFILE_ONLY is not None and name not in PROFILE_ONLY):
-        check(getattr(lib, name)(*args), name)
+        rc = fn(*args)
+        if rc != 0:
+            check(rc, name)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    rc = getattr(lib, name)(*args)
+    rc = fn(*args)
     e1.record()
     check(rc, name)
     PROFILE.setdefault(name, []).append((e0, e1, meta))
