@@ -50,8 +50,23 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug must trap (-> CUDA error on the host), never hang the GPU.
+// Bounded waits: a protocol bug must trap (-> CUDA error on the host), never hang the GPU.
+// mbar_wait: latency-critical handshakes.  Plain try_wait in a loop: a suspend-time hint parks the warp and was
+// measured to add ~1000 clk of wake-up latency per handshake on B200 (tools/micro/att_bench.cu traces).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 0xfffu) == 0) {
+      const uint64_t t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      if (t - t0 > 20000000000ull) __trap();  // 20 s
+    }
+  }
+}
+// mbar_wait_sleep: long waits of helper warps (loaders waiting for a buffer): parked in hardware, no issue slots.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait_hint(bar, parity, 2000000u)) return;
   const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait_hint(bar, parity, 2000000u)) {
@@ -66,6 +81,16 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes = 16) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// every cp.async this thread has issued (committed to a group or not) has landed
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// generic-proxy writes to shared memory (st.shared, landed cp.async) -> visible to the async proxy (tcgen05.mma, TMA)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -202,6 +227,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // registers -> TMEM (32 lanes x 16 columns)

@@ -176,8 +176,10 @@ def test_lang_head_and_losses_golden(golden):
 @pytest.mark.parametrize("H,d,K", [(2, 16, 1024), (3, 32, 1024), (2, 48, 1024), (4, 16, 256), (1, 48, 100)])
 def test_patch_attention_tensor_core(H, d, K):
     """tcgen05 kernel vs the fp32 oracle AND vs the independent SIMT kernel on the same bf16 inputs.
-    Tolerance: P is rounded to bf16 before P.V (2^-9 relative per term) and the result to bf16 (2^-9):
-    2e-2 absolute on outputs of magnitude <= ~1 (convex combinations of N(0,1) values)."""
+    Tolerance (bf16 has 8 significant bits): the softmax weights are cut to bf16 before P.V (<= 2^-8 relative
+    per weight, normalised by the sum of the SAME cut weights) and the result is rounded to bf16 (2^-9 relative):
+    |err| <= 8e-3 + 2^-7 |want| per element (outputs reach |x| ~ 6 on peaked rows, where one bf16 ulp is 0.03),
+    and 1e-2 in relative L2 over the tensor."""
     from scenesplat_b200 import ops
     rng = np.random.default_rng(1)
     offset = np.array([K // 2 + 3, K // 2 + 3 + 2 * K + 17, 4 * K + 40 + 333], dtype=np.int64)
@@ -194,9 +196,10 @@ def test_patch_attention_tensor_core(H, d, K):
     got = ops.patch_attention(qkv.cuda(), dev(order), table, K, H, scale, impl="tc")
     simt = ops.patch_attention(qkv.cuda(), dev(order), table, K, H, scale, impl="simt")
     torch.cuda.synchronize()
-    err = (got.float().cpu() - want).abs().max().item()
-    err_simt = (got.float() - simt.float()).abs().max().item()
-    assert err < 2e-2, err
-    assert err_simt < 2e-2, err_simt
+    tol = 8e-3 + 2.0 ** -7 * want.abs()
+    excess = ((got.float().cpu() - want).abs() - tol).max().item()
+    assert excess <= 0, excess
+    excess_simt = ((got.float() - simt.float()).abs().cpu() - tol).max().item()
+    assert excess_simt <= 0, excess_simt
     rel = ((got.float().cpu() - want).norm() / want.norm()).item()
     assert rel < 1e-2, rel
