@@ -4,26 +4,27 @@
 // and `feat[inverse]` gather (point_transformer_v3m1_base.py:181-216); patch rule of :114-170 comes in as
 // the device patch table (attention_simt.cu: patch_table_kernel).
 //
-// One CTA per (head, patch).  K and V of the head (<= 1024 tokens) stay resident in shared memory in the
-// UMMA no-swizzle core-matrix layout (K: K-major, V: MN-major), gathered once through the serialized
-// order with 16-byte cp.async, chunk by chunk behind per-chunk mbarriers so the first MMAs start while
-// the rest of K/V is still in flight.
+// One CTA per (head, patch), 12 warps.  K and V of the head (<= 1024 tokens) stay resident in shared memory in the
+// UMMA no-swizzle core-matrix layout (K: K-major, V: MN-major).  They are gathered through the serialized order
+// with 16-byte cp.async by the 8 softmax warps themselves (one 128-key chunk each, all in flight at once: those
+// warps have nothing else to do before the first S tile exists) behind per-chunk mbarriers.
 //
-// Single pass, online softmax, two query tiles of 128 rows in flight (ping-pong):
-//   warps 0-3  softmax group 0 (tiles 0, 2, 4, ..), warps 4-7 softmax group 1 (tiles 1, 3, ..): one thread
-//              owns one query row: the 128 scores of a key chunk come out of TMEM into registers, the
-//              row max / rescale decision / row sum are thread-local (no shuffles, no shared memory)
-//   warp 8     loader (cp.async gathers of Q tiles and K/V chunks -> mbarriers)
-//   warp 9     issues every tcgen05.mma: S_g = Q_g K_c^T, then O_g += P_g V_c with P as the TMEM A operand
-// While group 0 runs its exponentials the tensor pipe produces the next S of group 1 and vice versa, so
-// neither the MMA round trip nor the TMEM traffic is on the critical path; the kernel is bound by the
-// N*K*H exponentials (MUFU) for head dims 16..48, see DESIGN.md.
-// TMEM columns: S_0/P_0 [0,128)  S_1/P_1 [128,256)  O_0 [256,320)  O_1 [320,384).  P (bf16) overwrites the
-// first 64 columns of its own S tile; tcgen05.mma ops execute in issue order, so the next Q K^T of the
-// group may be queued right behind the P V that reads those columns.
-// Online softmax with lazy rescaling: the running reference max only moves when the chunk max exceeds it
-// by more than 2^8 (any shift cancels in O / l; bf16 / fp32 have the exponent range), so O is touched by
-// CUDA cores almost only on the first chunk(s) of a tile.
+// Single pass, online softmax, two query tiles of 128 rows in flight:
+//   warps 0-3   softmax group 0 (tiles 0, 2, 4, ..), warps 4-7 softmax group 1 (tiles 1, 3, ..): one thread owns
+//               one query row; the 128 scores of a key chunk come out of TMEM into registers, the row max and the
+//               rescale decision are thread-local (no shuffles, no shared memory)
+//   warps 8,11  Q loaders of group 0 / 1: the NEXT tile's rows are prefetched into registers and stored the moment
+//               the last Q K^T of the current tile has released the (single) Q buffer of the group
+//   warps 9,10  MMA issuers of group 0 / 1: S_g = Q_g K_c^T as soon as S_g of the previous step has been read into
+//               registers (s_free), O_g += P_g V_c and l_g += P_g 1 once P_g is written (p_ready)
+// TMEM columns: S_0 [0,128) S_1 [128,256) | P_0 [256,320) P_1 [320,384) (bf16 pairs) | O_0,l_0 [384,448) O_1,l_1
+// [448,512).  S and P are separate so the next Q K^T runs under the exponentials of the current step.
+// P is CUT to bf16 (no rounding instruction) and the row sum l is accumulated by the tensor core from the same
+// bf16 weights (P times a 16x16 tile of ones): O / l is an exactly normalised convex combination of V rows.
+// Online softmax with lazy rescaling: the running reference max only moves when the chunk max exceeds it by more
+// than 2^8 (any shift cancels in O / l; bf16 / fp32 have the exponent range), so O is touched by CUDA cores almost
+// only on the first chunk(s) of a tile.  The kernel is bound by the N*K*H exponentials, not by the tensor pipe
+// (see DESIGN.md); a fraction of them is evaluated on the FMA pipe (exp2_poly).
 #include <cstdlib>
 #include "tc_common.cuh"
 #include "../../include/scenesplat_b200.h"
@@ -40,7 +41,7 @@ constexpr int kOStride = 64;      // columns reserved per O tile (D of O, then t
 constexpr float kLazy = 8.f;      // log2 units the running max may lag behind
 
 #ifdef SS_ATT_TRACE  // developer instrumentation (tools/micro/att_bench.cu): clock64 stamps per CTA
-constexpr int kTraceSlots = 112, kTraceCtas = 2048;
+constexpr int kTraceSlots = 176, kTraceCtas = 2048;
 __device__ long long g_att_trace[kTraceCtas * kTraceSlots];
 #define ATT_TRACE(slot)                                                                             \
   do {                                                                                              \
@@ -68,16 +69,27 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max relative error 7.5e-5, 26x below the bf16 rounding of P), i added into the exponent field.
+// Needs x <= 126; anything below -126 (masked keys: -inf) comes out as 2^-126 * 0.99993 (a denormal: nothing next
+// to the row maximum's weight of >= 2^-8; the clamp keeps the exponent-field addition from borrowing into the sign).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05517166769f, 0.24261112209f);
+  p = fmaf(p, f, 0.69326098571f);
+  p = fmaf(p, f, 0.99992807355f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float y;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
   return y;
 }
 
-// VAR 0: P by cvt.rn.bf16x2 (F2FP), row sum by FADD
-// VAR 2: P truncated to bf16 (PRMT only), row sum on the tensor core (P times a ones tile -> l columns behind O):
-//        O / l is then an exactly normalised convex combination of the V rows with the weights actually used
-template <int D, int KMAX, int VAR>
+// POLY: of every 8 exponentials, POLY are evaluated by exp2_poly on the FMA pipe and 8 - POLY by MUFU.EX2
+template <int D, int KMAX, int POLY>
 __global__ void __launch_bounds__(kAttThreads, 1)
 patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ order_row,
                           const int4* __restrict__ table, int H, float scale_log2e, __nv_bfloat16* __restrict__ out) {
@@ -119,7 +131,7 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
     }
     tc::mbar_fence_init();
   }
-  if (VAR == 2 && threadIdx.x >= 256 && threadIdx.x < 384) {
+  if (threadIdx.x >= 256 && threadIdx.x < 384) {
     reinterpret_cast<uint32_t*>(smem + S::kOffOnes)[threadIdx.x - 256] = 0x3f803f80u;
     tc::fence_proxy_async();
   }
@@ -204,7 +216,6 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
     int s = 0;  // step counter of this group (phase of s_full / s_free / p_ready / pv_done)
     for (int i = 0; i < ntiles; ++i) {
       float msc = -INFINITY;  // running reference max (log2 domain, already scaled)
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       for (int j = 0; j < nch; ++j, ++s) {
         uint32_t v[4][32];
         tc::mbar_wait(&s_full[g], s & 1);
@@ -213,6 +224,7 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
         const bool tr_on = (warp & 3) == 0 && s >= 8 && s < 16;
         [[maybe_unused]] const int tr_base = 16 + g * 32 + (s - 8) * 4;
         if (tr_on) ATT_TRACE(tr_base);
+        if (g == 0 && s == 10) ATT_TRACE(156 + (warp & 3));
         tc::tmem_ld32(tS, v[0]);
         tc::tmem_ld32(tS + 32, v[1]);
         tc::tmem_ld32(tS + 64, v[2]);
@@ -243,12 +255,11 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
           const float newm = need ? nm : msc;
           const float f = ex2_approx(msc - newm);  // first chunk: exp2(-inf) = 0
           msc = newm;
-          l0 *= f; l1 *= f; l2 *= f; l3 *= f;
           if (j > 0) {
             tc::mbar_wait(&pv_done[g], (s - 1) & 1);  // O_g must be quiescent
             tc::tc_fence_after();
 #pragma unroll
-            for (int jo = 0; jo < (VAR == 2 ? D / 16 + 1 : D / 16); ++jo) {
+            for (int jo = 0; jo < D / 16 + 1; ++jo) {  // O columns and the row-sum columns behind them
               uint32_t o[16];
               tc::tmem_ld16(tO + jo * 16, o);
               tc::tmem_ld_wait();
@@ -259,42 +270,43 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
           }
         }
         if (tr_on) ATT_TRACE(tr_base + 2);
+        if (warp == 0 && s == 10) ATT_TRACE(163);
         const float nmsc = -msc;
         uint32_t pk[4][16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[q][2 * u]), scale_log2e, nmsc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[q][2 * u + 1]), scale_log2e, nmsc));
-            if (VAR == 0) {
-              if (u & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
-              pk[q][u] = tc::pack_bf16(p0, p1);
-            } else {
-              pk[q][u] = tc::pack_bf16_bits(__float_as_uint(p0), __float_as_uint(p1));
-            }
+            const float x0 = fmaf(__uint_as_float(v[q][2 * u]), scale_log2e, nmsc);
+            const float x1 = fmaf(__uint_as_float(v[q][2 * u + 1]), scale_log2e, nmsc);
+            const float p0 = ((2 * u) & 7) < POLY ? exp2_poly(x0) : ex2_approx(x0);
+            const float p1 = ((2 * u + 1) & 7) < POLY ? exp2_poly(x1) : ex2_approx(x1);
+            pk[q][u] = tc::pack_bf16_bits(__float_as_uint(p0), __float_as_uint(p1));  // truncation: see header
           }
         }
+        if (warp == 0 && s == 10) ATT_TRACE(160);
         if (j > 0) {  // P_g is still being read by the previous P V of the group (j == 0: the epilogue waited)
           tc::mbar_wait(&pv_done[g], (s - 1) & 1);
           tc::tc_fence_after();
         }
+        if (warp == 0 && s == 10) ATT_TRACE(161);
 #pragma unroll
         for (int q = 0; q < 4; ++q) tc::tmem_st16(tP + q * 16, pk[q]);  // keys 32q .. 32q+31 -> 16 packed columns
         tc::tmem_st_wait();
+        if (warp == 0 && s == 10) ATT_TRACE(162);
         tc::tc_fence_before();
         tc::mbar_arrive(&p_ready[g]);
         if (tr_on) ATT_TRACE(tr_base + 3);
+        if (warp == 0 && s == 7) ATT_TRACE(112);
+        if (g == 0 && s == 10) ATT_TRACE(152 + (warp & 3));
       }
       // ---- epilogue of the tile: O / l -> bf16 -> the point's own row (the [inverse] gather is fused)
       tc::mbar_wait(&pv_done[g], (s - 1) & 1);
       tc::tc_fence_after();
+      if (warp == 0 && i == 0) ATT_TRACE(113);
       const int qi = (2 * i + g) * kQB + row;
-      float lsum = (l0 + l1) + (l2 + l3);
-      if (VAR == 2) {
-        lsum = __uint_as_float(tc::tmem_ld1(tO + D));
-        tc::tmem_ld_wait();
-      }
+      const float lsum = __uint_as_float(tc::tmem_ld1(tO + D));  // sum of the bf16 weights, from the tensor core
+      tc::tmem_ld_wait();
       const float inv = 1.f / lsum;
       __nv_bfloat16* orow = nullptr;
       if (qi < n_q) orow = out + (size_t)order_row[q_beg + qi] * C + h * D;
@@ -326,14 +338,37 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
     // =========================================================== Q loaders (warp 8: group 0, warp 11: group 1)
     const int g = warp == 8 ? 0 : 1;
     const int ntiles = g == 0 ? (nqb + 1) / 2 : nqb / 2;
-    for (int i = 0; i < ntiles; ++i) {
-      if (i > 0) {
-        tc::mbar_wait_sleep(&q_free[g], (i - 1) & 1);
-        gather_q(2 * i + g);
+    // tile i = 0 was gathered straight into shared memory in the prologue
+    tc::cp_async_wait_all();
+    tc::fence_proxy_async();
+    tc::mbar_arrive(&q_full[g]);
+    // later tiles: the rows are fetched into REGISTERS while the previous tile of the group is still being
+    // processed, and stored the moment its last Q K^T has released the buffer (a third Q buffer does not fit
+    // beside K/V at head dim 48; a gather issued only then would expose ~3k cycles of latency per tile)
+    for (int i = 1; i < ntiles; ++i) {
+      const int t = 2 * i + g;
+      uint4 r[kItems];
+#pragma unroll
+      for (int u = 0; u < kItems; ++u) {
+        const int item = lane + 32 * u;
+        const int rr = item / kChunksPerRow, c = item - rr * kChunksPerRow;
+        const int qi = t * kQB + rr;
+        r[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (qi < n_q)
+          r[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)order_row[q_beg + qi] * (3 * C) + h * D + c * 8));
       }
-      tc::cp_async_wait_all();
+      tc::mbar_wait_sleep(&q_free[g], (i - 1) & 1);
+      if (g == 0 && i == 1) ATT_TRACE(115);
+      uint8_t* sQ = smem + S::kOffQ + g * S::kQ;
+#pragma unroll
+      for (int u = 0; u < kItems; ++u) {
+        const int item = lane + 32 * u;
+        const int rr = item / kChunksPerRow, c = item - rr * kChunksPerRow;
+        *reinterpret_cast<uint4*>(sQ + c * (kQB * 16) + (rr >> 3) * 128 + (rr & 7) * 16) = r[u];
+      }
       tc::fence_proxy_async();
       tc::mbar_arrive(&q_full[g]);
+      if (g == 0 && i == 1) ATT_TRACE(116);
     }
     if (warp == 8) ATT_TRACE(15);
   } else {
@@ -362,6 +397,7 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
       if (j == 0) {
         tc::mbar_wait(&q_full[g], tn & 1);
         tc::tc_fence_after();
+        if (g == 0 && tn == 1) ATT_TRACE(114);
       }
       if (kv_ready <= j) {
         tc::mbar_wait(&kv_full[j], 0);
@@ -389,10 +425,15 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
     if (total > 0) issue_qk();
     int pc = 0;  // chunk index of the next P V
     for (int s = 0; s < total; ++s) {
-      if (s + 1 < total) {
+      // Q K^T of the next step first (it only needs S_g to be in registers), unless it belongs to a new tile:
+      // then this step's P V must not queue behind the wait for the new Q rows
+      const bool qk_first = s + 1 < total && jn != 0;
+      if (qk_first) {
         tc::mbar_wait(&s_free[g], s & 1);
         tc::tc_fence_after();
+        if (s >= 8 && s < 16) ATT_TRACE(120 + (s - 8) * 4 + g * 2);
         issue_qk();
+        if (s >= 8 && s < 16) ATT_TRACE(120 + (s - 8) * 4 + g * 2 + 1);
       }
       tc::mbar_wait(&p_ready[g], s & 1);
       tc::tc_fence_after();
@@ -403,14 +444,15 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
         const uint64_t dv = dv_base | (uint64_t)((v0 + t * 16) & 0x3fff);
         tc::umma_bf16_ts_elect(tOg, tPg + 8 * t, dv, idesc_o, (pc | t) ? 1u : 0u);
       }
-      if (VAR == 2) {
 #pragma unroll
-        for (int t = 0; t < kKC / 16; ++t)
-          tc::umma_bf16_ts_elect(tOg + D, tPg + 8 * t, d_ones, idesc_l, (pc | t) ? 1u : 0u);
-      }
+      for (int t = 0; t < kKC / 16; ++t)
+        tc::umma_bf16_ts_elect(tOg + D, tPg + 8 * t, d_ones, idesc_l, (pc | t) ? 1u : 0u);
       tc::umma_commit_elect(&pv_done[g]);
       pc = pc == nch - 1 ? 0 : pc + 1;
       if (s >= 8 && s < 16) ATT_TRACE(80 + (s - 8) * 4 + g * 2 + 1);
+      if (s + 1 < total && !qk_first) {  // first Q K^T of the next tile (p_ready implies S_g was consumed)
+        issue_qk();
+      }
     }
     if (warp == 9) ATT_TRACE(14);
   }
@@ -423,12 +465,12 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
   }
 }
 
-template <int D, int VAR>
+template <int D, int POLY>
 static int launch_attention_var(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches,
                                 int heads, float scale, void* out, cudaStream_t stream) {
   constexpr int KMAX = 1024;
   using S = AttSmem<D, KMAX>;
-  auto kern = patch_attention_tc_kernel<D, KMAX, VAR>;
+  auto kern = patch_attention_tc_kernel<D, KMAX, POLY>;
   SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   // heads fastest: the H CTAs of a patch run together and share the gathered rows' DRAM sectors through L2
   dim3 grid((unsigned)((size_t)heads * max_patches));
@@ -441,11 +483,9 @@ static int launch_attention_var(const void* qkv, const int64_t* order_row, const
 template <int D>
 static int launch_attention(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches, int heads,
                             float scale, void* out, cudaStream_t stream) {
-  static const int var = getenv("SS_ATT_VAR") ? atoi(getenv("SS_ATT_VAR")) : 2;  // tuning hook
-  switch (var) {
-    case 0: return launch_attention_var<D, 0>(qkv, order_row, table, max_patches, heads, scale, out, stream);
-    default: return launch_attention_var<D, 2>(qkv, order_row, table, max_patches, heads, scale, out, stream);
-  }
+  static const int poly = getenv("SS_ATT_POLY") ? atoi(getenv("SS_ATT_POLY")) : 3;  // developer tuning hook
+  if (poly == 0) return launch_attention_var<D, 0>(qkv, order_row, table, max_patches, heads, scale, out, stream);
+  return launch_attention_var<D, 3>(qkv, order_row, table, max_patches, heads, scale, out, stream);
 }
 
 }  // namespace ss

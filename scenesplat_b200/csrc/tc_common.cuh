@@ -53,11 +53,18 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // Bounded waits: a protocol bug must trap (-> CUDA error on the host), never hang the GPU.
 // mbar_wait: latency-critical handshakes.  Plain try_wait in a loop: a suspend-time hint parks the warp and was
 // measured to add ~1000 clk of wake-up latency per handshake on B200 (tools/micro/att_bench.cu traces).
+#ifndef SS_MBAR_HINT_NS
+#define SS_MBAR_HINT_NS 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_fast(uint64_t* bar, uint32_t parity) {
+  if (SS_MBAR_HINT_NS == 0) return mbar_try_wait(bar, parity);
+  return mbar_try_wait_hint(bar, parity, SS_MBAR_HINT_NS);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait_fast(bar, parity)) return;
   uint64_t t0 = 0;
   for (uint32_t spins = 1;; ++spins) {
-    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait_fast(bar, parity)) return;
     if ((spins & 0xfffu) == 0) {
       const uint64_t t = global_timer_ns();
       if (t0 == 0) t0 = t;

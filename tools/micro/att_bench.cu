@@ -73,14 +73,21 @@ int main(int argc, char** argv) {
       return v[v.size() / 2];
     };
     for (int s = 1; s < 16; ++s) printf("  %-14s median %8lld clk\n", names[s], med(s, 0));
+    printf("  tile transition of group 0 (relative to its last p_ready arrival of tile 0): q_free seen by loader %lld, Q landed %lld, "
+           "pv_done seen %lld, epilogue end %lld, q_full seen by MMA %lld, next S seen %lld\n",
+           med(115, 112), med(116, 112), med(113, 112), med(11, 112), med(114, 112), med(16, 112));
     // second tile of each group (steady state): all relative to group 0's S-ready of step 8 (slot 16)
     printf("  step |  g0: S_seen ld_done max_done arrived |  g1: S_seen ld_done max_done arrived | mma: p0_seen p0_issued p1_seen p1_issued\n");
     for (int st = 0; st < 8; ++st) {
       printf("  %4d |", st + 8);
       for (int g = 0; g < 2; ++g) { for (int k = 0; k < 4; ++k) printf(" %7lld", med(16 + g * 32 + st * 4 + k, 16)); printf(" |"); }
       for (int k = 0; k < 4; ++k) printf(" %7lld", med(80 + st * 4 + k, 16));
+      printf(" | sfree/qk g0 %7lld %7lld g1 %7lld %7lld", med(120 + st * 4, 16), med(121 + st * 4, 16), med(122 + st * 4, 16), med(123 + st * 4, 16));
       printf("\n");
     }
+    printf("  warp 0 step 10 (rel. to exp start): exps done %lld, pv_done passed %lld, STTM done %lld, arrived %lld\n", med(160, 163), med(161, 163), med(162, 163), med(152, 163));
+    printf("  group 0 step 10, warps 0..3: S_seen %lld %lld %lld %lld  arrived %lld %lld %lld %lld\n", med(156, 16), med(157, 16), med(158, 16),
+           med(159, 16), med(152, 16), med(153, 16), med(154, 16), med(155, 16));
   }
 #endif
   return 0;
