@@ -127,6 +127,11 @@ int ss_subm_conv_simt(const void* in, int in_is_bf16, const int32_t* nbr, const 
 int ss_subm_conv_gemm(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
                       int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream);
 
+/* Same product, second-generation kernel: persistent CTAs, 256-row tiles (two M=128 accumulators share every
+ * W stage).  tile_tap [p_pad/256] gives the tap of every 256-row tile; every tap segment is padded to 256 rows. */
+int ss_subm_conv_gemm256(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
+                         int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream);
+
 /* out[p,:] = bias + sum_t prod[ypos[t][p], :]  (fp32 accumulate) -> bf16/fp32 */
 int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float* bias, int64_t n, int k3, int cout,
                         void* out, int out_is_bf16, void* stream);

@@ -5,6 +5,8 @@ computation itself (the CUDA library is the only implementation).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -166,9 +168,13 @@ def kmap_build(grid_coord, batch, code_row, order_row, depth: int, order_id: int
     return nbr, cnt
 
 
-def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = 128):
+CONV_TILE = int(os.environ.get("SS_CONV_TILE", "256"))  # rows per gather-GEMM tile (128: first-generation kernel)
+
+
+def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = None):
     """Pair lists for the gather-GEMM conv.  -> dict(pair_in [p_pad] i32, ypos [k^3, n] i32, tile_tap [p_pad/tile] i32,
-    p_pad, pairs)."""
+    p_pad, pairs, tile).  Every tap's segment is padded to a multiple of `tile` rows."""
+    tile = tile or CONV_TILE
     k3, n = nbr.shape
     dev = nbr.device
     base, tile_tap, o = [], [], 0
@@ -185,7 +191,7 @@ def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = 128):
     L.call("ss_kmap_pairs", L.ptr(nbr), L.ptr(order_row.contiguous()), n, k, L.ptr(base_dev), p_pad, L.ptr(pair_in),
            L.ptr(ypos), L.ptr(ws), ws.numel(), L.stream())
     return dict(pair_in=pair_in, ypos=ypos, tile_tap=torch.tensor(tile_tap or [0], dtype=torch.int32, device=dev),
-                p_pad=p_pad, pairs=int(sum(int(c) for c in tap_count_host)))
+                p_pad=p_pad, pairs=int(sum(int(c) for c in tap_count_host)), tile=tile)
 
 
 def subm_conv_simt(x, nbr, wt, bias=None, scale=None, shift=None, act=0, out_dtype=None):
@@ -204,7 +210,8 @@ def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16
     k3, cout, cin = w_bf16.shape
     p_pad = pairs["p_pad"]
     prod = torch.empty((max(p_pad, 1), cout), dtype=_BF16, device=x_bf16.device)
-    L.call("ss_subm_conv_gemm", L.ptr(x_bf16.contiguous()), L.ptr(pairs["pair_in"]), L.ptr(w_bf16),
+    fn = "ss_subm_conv_gemm256" if pairs.get("tile", 128) == 256 else "ss_subm_conv_gemm"
+    L.call(fn, L.ptr(x_bf16.contiguous()), L.ptr(pairs["pair_in"]), L.ptr(w_bf16),
            L.ptr(pairs["tile_tap"]), p_pad, k3, cin, cout, L.ptr(prod), L.stream(),
            meta=dict(flops=2.0 * pairs["pairs"] * cin * cout, bytes=2.0 * pairs["pairs"] * (cin + cout)))
     out = torch.empty((n, cout), dtype=out_dtype, device=x_bf16.device)

@@ -56,8 +56,10 @@ def test_subm_conv_simt(k, cin, cout, bias):
     np.testing.assert_allclose(got2.cpu().numpy(), F.gelu(want * scale + shift).numpy(), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("tile", [128, 256])
 @pytest.mark.parametrize("c", [32, 64, 128, 256, 768])
-def test_subm_conv_tensor_core(c):
+def test_subm_conv_tensor_core(c, tile):
+    """tile = 128: first-generation gather-GEMM (one M tile per CTA); 256: persistent two-accumulator kernel."""
     from scenesplat_b200 import ops
     g, batch, offset, code, order, inv, depth = _scene(6000 if c > 256 else 12000)
     torch.manual_seed(1)
@@ -68,7 +70,7 @@ def test_subm_conv_tensor_core(c):
     nbr_ref = oconv.kernel_map(g, batch, 3)
     want = oconv.subm_conv(x.float(), nbr_ref, w.float(), b)
     nbr, cnt = ops.kmap_build(dev(g), dev(batch), dev(code[0]), dev(order[0]), depth, 0, 3)
-    pairs = ops.kmap_pairs(nbr, dev(order[0]), 3, cnt.cpu().numpy())
+    pairs = ops.kmap_pairs(nbr, dev(order[0]), 3, cnt.cpu().numpy(), tile=tile)
     wk = w.reshape(c, 27, c).permute(1, 0, 2).contiguous().cuda()  # [27, cout, cin]
     got = ops.subm_conv_gemm(x.cuda(), pairs, wk, b.cuda(), n, out_dtype=torch.float32)
     err = (got.cpu() - want).abs().max().item()

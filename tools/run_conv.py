@@ -1,0 +1,53 @@
+"""Stand-alone driver of the tcgen05 gather-GEMM conv at a lang-config shape (developer tool for timing / ncu)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from scenesplat_b200 import ops, synthetic
+from oracle import gridsample as ogs, serialization as oser
+
+n_raw = int(os.environ.get("CONV_NRAW", 360000))
+c = int(os.environ.get("CONV_C", 768))
+reps = int(os.environ.get("CONV_REPS", 5))
+d = synthetic.chunk(n_raw, L=6.0, H=3.0, seed=0)
+res = ogs.grid_sample_train(d["coord"], 0.02)
+g = res["grid_coord"]
+n = g.shape[0]
+offset = np.array([n], dtype=np.int64)
+batch = oser.offset2batch(offset)
+code, order, inv, depth = oser.serialization(g, batch, 1, ("z",))
+dev = lambda a: torch.as_tensor(a).cuda()
+nbr, cnt = ops.kmap_build(dev(g), dev(batch), dev(code[0]), dev(order[0]), depth, 0, 3)
+torch.manual_seed(0)
+x = torch.randn(n, c, device="cuda").bfloat16()
+w = (torch.randn(27, c, c, device="cuda") * 0.01).bfloat16()
+b = torch.zeros(c, device="cuda")
+for tile in (128, 256):
+    pairs = ops.kmap_pairs(nbr, dev(order[0]), 3, cnt.cpu().numpy(), tile=tile)
+    fn = "ss_subm_conv_gemm256" if tile == 256 else "ss_subm_conv_gemm"
+    prod = torch.empty((pairs["p_pad"], c), dtype=torch.bfloat16, device="cuda")
+    from scenesplat_b200 import _lib as L
+    def run():
+        L.call(fn, L.ptr(x), L.ptr(pairs["pair_in"]), L.ptr(w), L.ptr(pairs["tile_tap"]), pairs["p_pad"], 27, c, c,
+               L.ptr(prod), L.stream())
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fl = 2.0 * pairs["pairs"] * c * c
+    print(f"n={n} C={c} tile={tile}: pairs {pairs['pairs']} (padded {pairs['p_pad']}) gemm {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s useful")
+    if tile == 128:
+        ref = prod[: pairs["p_pad"]].clone()
+        ypos128 = pairs["ypos"]
+    else:
+        # compare through the pair positions (the two paddings differ)
+        a = ref[ypos128.clamp_min(0).long().flatten()].float()
+        bb = prod[pairs["ypos"].clamp_min(0).long().flatten()].float()
+        m = (ypos128.flatten() >= 0)
+        print("   max |tile256 - tile128| over active pairs:", (a[m] - bb[m]).abs().max().item())
