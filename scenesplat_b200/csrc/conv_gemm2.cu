@@ -12,9 +12,9 @@
 // neighbouring SMs at the same time and their identical A gathers hit L2.
 //
 // 14 warps:  0-3  epilogue (TMEM -> bf16 -> shared-memory transpose -> 64-byte coalesced global stores)
-//            4-11 A producers: 16-byte cp.async gathers into 128B-swizzled K-major tiles; each thread
-//                 publishes a stage with cp.async.wait_group + fence.proxy.async + mbarrier arrive, LAG stages
-//                 behind its issue point, so the gathers of LAG + 1 stages are in flight per thread
+//            4-11 A producers: 16-byte cp.async gathers into 128B-swizzled K-major tiles, published per thread with
+//                 cp.async.mbarrier.arrive.noinc (the arrival fires when the thread's copies have landed; a
+//                 wait_group + fence + arrive chain was measured to serialise MMA k behind MMA k-1)
 //            12   W producer (TMA, one lane)       13   MMA issuer (tcgen05.mma M128 x N=BN x K16, 8 per stage)
 // The producers run ahead into the next work item while the epilogue drains the accumulators.
 #include "tc_common.cuh"
@@ -43,7 +43,6 @@ gather_gemm256_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __rest
                       const __grid_constant__ CUtensorMap tmap_w, const int32_t* __restrict__ tile_tap, int cin, int cout,
                       int n_slabs, int64_t n_items, __nv_bfloat16* __restrict__ prod) {
   using S = Gemm2Smem<BN, STAGES>;
-  constexpr int LAG = STAGES - 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + S::kOffBar);  // [STAGES] 256 gather threads + 1 TMA expect_tx arrive
@@ -94,18 +93,11 @@ gather_gemm256_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __rest
                            X + (size_t)rows[i] * cin + k0 + c * 8);
           }
         }
-        tc::cp_async_commit();
-        if (g >= LAG) {
-          tc::cp_async_wait<LAG>();
-          tc::fence_proxy_async();
-          tc::mbar_arrive(&full_bar[(g - LAG) % STAGES]);
-        }
+        // the stage is published by the copies themselves (arrive when this thread's cp.asyncs have landed):
+        // the thread never blocks on its own data, so STAGES stages of gathers are in flight
+        tc::cp_async_mbar_arrive_noinc(&full_bar[s]);
       }
     }
-    // drain: publish the last LAG stages
-    tc::cp_async_wait_all();
-    tc::fence_proxy_async();
-    for (int64_t d = (g >= LAG ? g - LAG : 0); d < g; ++d) tc::mbar_arrive(&full_bar[d % STAGES]);
   } else if (warp == 12) {
     // ------------------------------------------------------------------ W producer (TMA, one lane)
     if (lane == 0) {
