@@ -202,8 +202,10 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
   }
 }
 
-// out[p, :] = bias + sum_t prod[ypos[t][p], :]; one warp per output voxel, 16-byte (8 x bf16) lanes.
-template <typename TO>
+// out[p, :] = bias + sum_t prod[ypos[t][p], :]; one warp per output voxel, 16-byte (8 x bf16) lanes, J x 256
+// channels per pass.  The voxel's k3 product-row positions are fetched with ONE load (lane = tap), the active ones
+// are walked in ascending tap order (fixed summation order) four at a time so four row loads are in flight per lane.
+template <typename TO, int J>
 __global__ void __launch_bounds__(256)
 conv_reduce_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __restrict__ ypos,
                    const float* __restrict__ bias, int64_t n, int k3, int cout, TO* __restrict__ out) {
@@ -211,33 +213,64 @@ conv_reduce_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __rest
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t p = warp0; p < n; p += nwarp) {
-    for (int c0 = lane * 8; c0 < cout; c0 += 256) {
-      float acc[8];
+    float acc[J][8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] = bias ? bias[c0 + u] : 0.f;
-      for (int t = 0; t < k3; ++t) {
-        const int32_t pos = ypos[(size_t)t * n + p];
-        if (pos < 0) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(prod + (size_t)pos * cout + c0);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    for (int j = 0; j < J; ++j) {
+      const int c0 = j * 256 + lane * 8;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float2 f = __bfloat1622float2(h[u]);
-          acc[2 * u] += f.x;
-          acc[2 * u + 1] += f.y;
+      for (int u = 0; u < 8; ++u) acc[j][u] = (bias && c0 < cout) ? bias[c0 + u] : 0.f;
+    }
+    for (int t0 = 0; t0 < k3; t0 += 32) {
+      const int32_t mypos = (t0 + lane < k3) ? ypos[(size_t)(t0 + lane) * n + p] : -1;
+      uint32_t m = __ballot_sync(0xffffffffu, mypos >= 0);
+      while (m) {
+        int32_t pos[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int t = m ? __ffs(m) - 1 : 0;
+          pos[q] = m ? __shfl_sync(0xffffffffu, mypos, t) : -1;
+          m &= m - 1;  // (0 stays 0)
+        }
+        uint4 v[4][J];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const int c0 = j * 256 + lane * 8;
+            v[q][j] = make_uint4(0u, 0u, 0u, 0u);
+            if (pos[q] >= 0 && c0 < cout) v[q][j] = *reinterpret_cast<const uint4*>(prod + (size_t)pos[q] * cout + c0);
+          }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (pos[q] < 0) continue;  // warp-uniform; (adding the zero vector would turn a -0 sum into +0)
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[q][j]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = __bfloat1622float2(h[u]);
+              acc[j][2 * u] += f.x;
+              acc[j][2 * u + 1] += f.y;
+            }
+          }
         }
       }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      if (c0 >= cout) continue;
       if constexpr (sizeof(TO) == 2) {
         uint4 o;
-        o.x = tc::pack_bf16(acc[0], acc[1]);
-        o.y = tc::pack_bf16(acc[2], acc[3]);
-        o.z = tc::pack_bf16(acc[4], acc[5]);
-        o.w = tc::pack_bf16(acc[6], acc[7]);
+        o.x = tc::pack_bf16(acc[j][0], acc[j][1]);
+        o.y = tc::pack_bf16(acc[j][2], acc[j][3]);
+        o.z = tc::pack_bf16(acc[j][4], acc[j][5]);
+        o.w = tc::pack_bf16(acc[j][6], acc[j][7]);
         *reinterpret_cast<uint4*>(out + (size_t)p * cout + c0) = o;
       } else {
         float4* o = reinterpret_cast<float4*>(out + (size_t)p * cout + c0);
-        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        o[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        o[1] = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
       }
     }
   }
@@ -318,13 +351,22 @@ int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float*
   if (n < 0 || k3 < 1 || cout < 8 || cout % 8 != 0) return SS_BAD_ARGS;
   if (n == 0) return SS_OK;
   if (!prod_bf16 || !ypos || !out) return SS_BAD_ARGS;
+  if (cout > 1024) return SS_BAD_ARGS;
   const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8), 32 * ss::kNumSMs);
-  if (out_is_bf16)
-    ss::conv_reduce_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)prod_bf16, ypos, bias, n, k3,
-                                                                      cout, (__nv_bfloat16*)out);
-  else
-    ss::conv_reduce_kernel<float><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)prod_bf16, ypos, bias, n, k3, cout,
-                                                              (float*)out);
+  const int j = (cout + 255) / 256;
+#define SS_RED_(TO, J) \
+  ss::conv_reduce_kernel<TO, J><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)prod_bf16, ypos, bias, n, k3, cout, (TO*)out)
+#define SS_RED_J_(TO)                 \
+  do {                                \
+    if (j == 1) SS_RED_(TO, 1);       \
+    else if (j == 2) SS_RED_(TO, 2);  \
+    else if (j == 3) SS_RED_(TO, 3);  \
+    else SS_RED_(TO, 4);              \
+  } while (0)
+  if (out_is_bf16) SS_RED_J_(__nv_bfloat16);
+  else SS_RED_J_(float);
+#undef SS_RED_J_
+#undef SS_RED_
   SS_CHECK_LAUNCH();
   return SS_OK;
 }

@@ -17,7 +17,7 @@ template <typename T> __device__ __forceinline__ T cvt_out(float v);
 template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
-__device__ __forceinline__ float gelu_erf_(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_(float x) { return gelu_fast(x); }
 
 // One warp per output voxel; lane owns output channels lane + 32u (u < UMAX => Cout <= 32*UMAX).
 template <typename TI, typename TO, int UMAX>
@@ -64,6 +64,59 @@ subm_conv_simt_kernel(const TI* __restrict__ in, const int32_t* __restrict__ nbr
   }
 }
 
+// Small-channel variant (the stem: 5^3 taps, Cin = 11 -> Cout = 32): one warp per 32 CONSECUTIVE voxels.
+// lane = voxel for the loads (the 125 neighbour-table reads are coalesced 128-byte rows, the 11-float input rows of
+// a tap are fetched by all lanes at once: one memory latency per tap instead of one per (tap, voxel) pair),
+// lane = output channel for the arithmetic (input values are broadcast with shuffles, the tap's weights sit in
+// registers and are reused by the 32 voxels).  acc[i] = output row of voxel i, channel `lane`.
+template <typename TI, typename TO, int CIN>
+__global__ void __launch_bounds__(256)
+subm_conv_small_kernel(const TI* __restrict__ in, const int32_t* __restrict__ nbr, const float* __restrict__ wt,
+                       const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                       int act, int64_t n, int k3, int cin, int cout, TO* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p0 = warp0 * 32; p0 < n; p0 += nwarp * 32) {
+    const int64_t p = p0 + lane;
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int t = 0; t < k3; ++t) {
+      const int32_t q = p < n ? nbr[(size_t)t * n + p] : -1;
+      const uint32_t mask = __ballot_sync(0xffffffffu, q >= 0);
+      if (mask == 0u) continue;
+      float x[CIN], w[CIN];
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        x[ci] = (q >= 0 && ci < cin) ? cvt_in<TI>(in[(size_t)q * cin + ci]) : 0.f;
+        w[ci] = (ci < cin && lane < cout) ? __ldg(wt + ((size_t)t * cin + ci) * cout + lane) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if ((mask >> i) & 1u) {  // warp-uniform
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci)
+            if (ci < cin) acc[i] = fmaf(__shfl_sync(0xffffffffu, x[ci], i), w[ci], acc[i]);
+        }
+      }
+    }
+    if (lane < cout) {
+      const float b = bias ? bias[lane] : 0.f;
+      const float sc = scale ? scale[lane] : 1.f, sh = scale ? shift[lane] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (p0 + i < n) {
+          float v = acc[i] + b;
+          if (scale) v = v * sc + sh;
+          if (act == 1) v = gelu_erf_(v);
+          out[(size_t)(p0 + i) * cout + lane] = cvt_out<TO>(v);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ss
 
 extern "C" int ss_subm_conv_simt(const void* in, int in_is_bf16, const int32_t* nbr, const float* wt, const float* bias,
@@ -73,6 +126,19 @@ extern "C" int ss_subm_conv_simt(const void* in, int in_is_bf16, const int32_t* 
   if (n < 0 || k3 < 1 || cin < 1 || cout < 1 || cout > 1024 || (scale && !shift)) return SS_BAD_ARGS;
   if (n == 0) return SS_OK;
   if (!in || !nbr || !wt || !out) return SS_BAD_ARGS;
+  if (cin <= 16 && cout <= 32) {  // stem-like shapes: warp per 32 voxels
+    const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8 * 32), 8 * ss::kNumSMs);
+#define SS_SMALL_(TI, TO)                                                                                          \
+  ss::subm_conv_small_kernel<TI, TO, 16><<<blocks, 256, 0, stream>>>((const TI*)in, nbr, wt, bias, scale, shift, act, \
+                                                                     n, k3, cin, cout, (TO*)out)
+    if (in_is_bf16 && out_is_bf16) SS_SMALL_(__nv_bfloat16, __nv_bfloat16);
+    else if (in_is_bf16) SS_SMALL_(__nv_bfloat16, float);
+    else if (out_is_bf16) SS_SMALL_(float, __nv_bfloat16);
+    else SS_SMALL_(float, float);
+#undef SS_SMALL_
+    SS_CHECK_LAUNCH();
+    return SS_OK;
+  }
   const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8), 32 * ss::kNumSMs);
 #define SS_LAUNCH_(TI, TO, U)                                                                                     \
   ss::subm_conv_simt_kernel<TI, TO, U><<<blocks, 256, 0, stream>>>((const TI*)in, nbr, wt, bias, scale, shift, act, n, \

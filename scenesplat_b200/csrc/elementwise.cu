@@ -14,7 +14,7 @@ template <typename T> __device__ __forceinline__ T e_out(float v);
 template <> __device__ __forceinline__ float e_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 e_out<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
-__device__ __forceinline__ float e_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float e_gelu(float x) { return gelu_fast(x); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -126,7 +126,10 @@ def test_add_layernorm_and_friends():
     x = torch.randn(1000, 64)
     s, t = torch.rand(64) + 0.5, torch.randn(64)
     got = ops.affine_act(x.cuda(), s.cuda(), t.cuda(), act=1)
-    np.testing.assert_allclose(got.cpu().numpy(), F.gelu(x * s + t).numpy(), rtol=1e-5, atol=1e-6)
+    # erf-GELU evaluated in float64 on the SAME fp32 affine result: the kernel's gelu_fast is within 3.3e-7 of it
+    # (torch's own fp32 erf-GELU is only within 1.2e-6), so 1e-6 absolute
+    want = F.gelu((x * s + t).double()).float()
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
     xb = torch.randn(1000, 256).bfloat16()
     got = ops.affine_act(xb.cuda(), act=1)
     np.testing.assert_allclose(got.float().cpu().numpy(), F.gelu(xb.float()).bfloat16().float().numpy(), rtol=1e-2,
