@@ -69,11 +69,12 @@ subm_conv_simt_kernel(const TI* __restrict__ in, const int32_t* __restrict__ nbr
 // a tap are fetched by all lanes at once: one memory latency per tap instead of one per (tap, voxel) pair),
 // lane = output channel for the arithmetic (input values are broadcast with shuffles, the tap's weights sit in
 // registers and are reused by the 32 voxels).  acc[i] = output row of voxel i, channel `lane`.
-template <typename TI, typename TO, int CIN>
+template <typename TI, typename TO, int CIN, bool EXACT>  // EXACT: cin == CIN (no per-channel predicates)
 __global__ void __launch_bounds__(256)
 subm_conv_small_kernel(const TI* __restrict__ in, const int32_t* __restrict__ nbr, const float* __restrict__ wt,
                        const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
-                       int act, int64_t n, int k3, int cin, int cout, TO* __restrict__ out) {
+                       int act, int64_t n, int k3, int cin_rt, int cout, TO* __restrict__ out) {
+  const int cin = EXACT ? CIN : cin_rt;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -82,22 +83,28 @@ subm_conv_small_kernel(const TI* __restrict__ in, const int32_t* __restrict__ nb
     float acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    int32_t q_next = p < n ? nbr[p] : -1;  // tap 0; the table read of tap t + 1 is issued before tap t's arithmetic
     for (int t = 0; t < k3; ++t) {
-      const int32_t q = p < n ? nbr[(size_t)t * n + p] : -1;
+      const int32_t q = q_next;
+      if (t + 1 < k3) q_next = p < n ? nbr[(size_t)(t + 1) * n + p] : -1;
       const uint32_t mask = __ballot_sync(0xffffffffu, q >= 0);
       if (mask == 0u) continue;
       float x[CIN], w[CIN];
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
-        x[ci] = (q >= 0 && ci < cin) ? cvt_in<TI>(in[(size_t)q * cin + ci]) : 0.f;
-        w[ci] = (ci < cin && lane < cout) ? __ldg(wt + ((size_t)t * cin + ci) * cout + lane) : 0.f;
+        x[ci] = (q >= 0 && (EXACT || ci < cin)) ? cvt_in<TI>(in[(size_t)q * cin + ci]) : 0.f;
+        w[ci] = ((EXACT || ci < cin) && lane < cout) ? __ldg(wt + ((size_t)t * cin + ci) * cout + lane) : 0.f;
       }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if ((mask >> i) & 1u) {  // warp-uniform
+      for (int g4 = 0; g4 < 8; ++g4) {
+        if (((mask >> (4 * g4)) & 0xfu) == 0u) continue;  // warp-uniform
 #pragma unroll
-          for (int ci = 0; ci < CIN; ++ci)
-            if (ci < cin) acc[i] = fmaf(__shfl_sync(0xffffffffu, x[ci], i), w[ci], acc[i]);
+        for (int i = 4 * g4; i < 4 * g4 + 4; ++i) {
+          if ((mask >> i) & 1u) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+              if (EXACT || ci < cin) acc[i] = fmaf(__shfl_sync(0xffffffffu, x[ci], i), w[ci], acc[i]);
+          }
         }
       }
     }
@@ -128,9 +135,15 @@ extern "C" int ss_subm_conv_simt(const void* in, int in_is_bf16, const int32_t* 
   if (!in || !nbr || !wt || !out) return SS_BAD_ARGS;
   if (cin <= 16 && cout <= 32) {  // stem-like shapes: warp per 32 voxels
     const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8 * 32), 8 * ss::kNumSMs);
-#define SS_SMALL_(TI, TO)                                                                                          \
-  ss::subm_conv_small_kernel<TI, TO, 16><<<blocks, 256, 0, stream>>>((const TI*)in, nbr, wt, bias, scale, shift, act, \
-                                                                     n, k3, cin, cout, (TO*)out)
+#define SS_SMALL_(TI, TO)                                                                                            \
+  do {                                                                                                               \
+    if (cin == 11)                                                                                                   \
+      ss::subm_conv_small_kernel<TI, TO, 11, true><<<blocks, 256, 0, stream>>>((const TI*)in, nbr, wt, bias, scale,   \
+                                                                               shift, act, n, k3, cin, cout, (TO*)out); \
+    else                                                                                                             \
+      ss::subm_conv_small_kernel<TI, TO, 16, false><<<blocks, 256, 0, stream>>>((const TI*)in, nbr, wt, bias, scale,  \
+                                                                                shift, act, n, k3, cin, cout, (TO*)out); \
+  } while (0)
     if (in_is_bf16 && out_is_bf16) SS_SMALL_(__nv_bfloat16, __nv_bfloat16);
     else if (in_is_bf16) SS_SMALL_(__nv_bfloat16, float);
     else if (out_is_bf16) SS_SMALL_(float, __nv_bfloat16);
