@@ -44,6 +44,8 @@ LANG_BACKBONE = dict(
 N_RAW = 360000          # -> 299,277 voxels after GridSample(0.02) on the synthetic room (seed 0)
 CPU_SAMPLE_RAW = 120000  # bounded CPU sample: a ~100k-voxel sub-chunk of the same generator (10-30 s of CPU work)
 METRIC = "gaussians_per_s_ptv3_fwd"
+MUFU_PEAK_TEXP = 4.63                     # measured ex2 throughput of one B200, T/s (tools/micro/mufu.cu)
+ATTENTION_DRAM_BYTES_PER_LAUNCH = 290.4e6  # ncu dram read+write, mean of the 18 launches of a step (profiles/r1_launches_v2.md)
 UNIT = "Gaussians/s"
 
 
@@ -308,7 +310,7 @@ def main():
             ms = float(t.item())
         return ms, prof, launches, clocks
 
-    hot = frozenset({"ss_patch_attention", "ss_subm_conv_gemm"})  # the two candidates for "dominant own kernel"
+    hot = frozenset({"ss_patch_attention", "ss_subm_conv_gemm", "ss_subm_conv_gemm256"})  # the two candidates for "dominant own kernel"
     ms, prof_hot, launches, clocks = timed(step_resident, args.steps, profile=hot)
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
     # full per-kernel table from a separate instrumented pass (events around ~350 calls/step perturb the step)
@@ -329,7 +331,8 @@ def main():
         for name, recs in (p or {}).items():
             tms = sum(a.elapsed_time(b) for a, b, _ in recs)
             t[name] = dict(ms=tms, calls=len(recs), flops=sum((m or {}).get("flops", 0.0) for _, _, m in recs),
-                           bytes=sum((m or {}).get("bytes", 0.0) for _, _, m in recs))
+                           bytes=sum((m or {}).get("bytes", 0.0) for _, _, m in recs),
+                           exps=sum((m or {}).get("exps", 0.0) for _, _, m in recs))
         return t
 
     table = tabulate(prof)          # all calls, separate pass (prof_steps steps)
@@ -344,6 +347,16 @@ def main():
             roofline = dict(kernel=name, bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s",
                             frac=ach / pk["tf_sust"], traffic=None, peak_source=pk["src"] + " (sustained bf16)",
                             share_of_step=r["ms"] / ms, calls_per_step=r["calls"] / args.steps)
+            if name == "ss_patch_attention":
+                # measured once per kernel version with ncu (profiles/r1_attention_ncu.md): DRAM bytes per launch,
+                # averaged over the 18 launches of a step like `achieved`
+                roofline["traffic"] = ATTENTION_DRAM_BYTES_PER_LAUNCH
+                # the binding pipe at head dims 16..48 is MUFU (one exponential per score), not the tensor pipe:
+                # 4 d FLOPs per exponential caps the FLOP rate at 4 d x the MUFU rate (d = 48: 0.89 PFLOP/s)
+                exp_rate = r["exps"] / (r["ms"] * 1e-3)
+                roofline["binding_pipe"] = dict(pipe="MUFU.EX2", achieved=exp_rate / 1e12, peak=MUFU_PEAK_TEXP, unit="Texp/s",
+                                                frac=exp_rate / 1e12 / MUFU_PEAK_TEXP,
+                                                peak_source="measured, tools/micro/mufu.cu (16 / clk / SM at 1.955 GHz)")
         else:
             ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
             roofline = dict(kernel=name, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],

@@ -92,7 +92,8 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 template <int D, int KMAX, int POLY>
 __global__ void __launch_bounds__(kAttThreads, 1)
 patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ order_row,
-                          const int4* __restrict__ table, int H, float scale_log2e, __nv_bfloat16* __restrict__ out) {
+                          const int4* __restrict__ table, int H, float scale_log2e, __nv_bfloat16* __restrict__ out,
+                          int stagger_on) {
   using S = AttSmem<D, KMAX>;
   const int4 e = table[blockIdx.x / H];
   const int q_beg = e.x, n_q = e.y - e.x, kv_beg = e.z, kv_len = e.w - e.z;
@@ -116,6 +117,7 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
   const int C = H * D;
   const int nch = (kv_len + kKC - 1) / kKC;  // key chunks
   const int nqb = (n_q + kQB - 1) / kQB;     // query tiles
+  const bool stagger = stagger_on && nqb > 1;  // both groups have work
   constexpr int kChunksPerRow = D / 8;       // 16-byte pieces per row
   constexpr int kItems = 4 * kChunksPerRow;  // pieces per lane per unit of 128 rows
 
@@ -216,6 +218,8 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
     int s = 0;  // step counter of this group (phase of s_full / s_free / p_ready / pv_done)
     for (int i = 0; i < ntiles; ++i) {
       float msc = -INFINITY;  // running reference max (log2 domain, already scaled)
+      const int qi = (2 * i + g) * kQB + row;
+      const int64_t out_row = qi < n_q ? order_row[q_beg + qi] : -1;  // fetched now, needed by the tile's epilogue
       for (int j = 0; j < nch; ++j, ++s) {
         uint32_t v[4][32];
         tc::mbar_wait(&s_full[g], s & 1);
@@ -271,6 +275,9 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
         }
         if (tr_on) ATT_TRACE(tr_base + 2);
         if (warp == 0 && s == 10) ATT_TRACE(163);
+        // One-time stagger: group 1 starts its first exponentials only when group 0 has finished its own, so the
+        // groups settle half a step apart: one runs its MUFU burst while the other is in its TMEM / handshake part.
+        if (stagger && s == 0 && g == 1) asm volatile("bar.sync 2, 256;" ::: "memory");
         const float nmsc = -msc;
         uint32_t pk[4][16];
 #pragma unroll
@@ -285,6 +292,7 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
           }
         }
         if (warp == 0 && s == 10) ATT_TRACE(160);
+        if (stagger && s == 0 && g == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
         if (j > 0) {  // P_g is still being read by the previous P V of the group (j == 0: the epilogue waited)
           tc::mbar_wait(&pv_done[g], (s - 1) & 1);
           tc::tc_fence_after();
@@ -304,12 +312,10 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
       tc::mbar_wait(&pv_done[g], (s - 1) & 1);
       tc::tc_fence_after();
       if (warp == 0 && i == 0) ATT_TRACE(113);
-      const int qi = (2 * i + g) * kQB + row;
       const float lsum = __uint_as_float(tc::tmem_ld1(tO + D));  // sum of the bf16 weights, from the tensor core
       tc::tmem_ld_wait();
       const float inv = 1.f / lsum;
-      __nv_bfloat16* orow = nullptr;
-      if (qi < n_q) orow = out + (size_t)order_row[q_beg + qi] * C + h * D;
+      __nv_bfloat16* orow = out_row >= 0 ? out + (size_t)out_row * C + h * D : nullptr;
 #pragma unroll
       for (int jo = 0; jo < D / 16; ++jo) {
         uint32_t o[16];
@@ -468,6 +474,7 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
 template <int D, int POLY>
 static int launch_attention_var(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches,
                                 int heads, float scale, void* out, cudaStream_t stream) {
+  static const int stagger = getenv("SS_ATT_STAGGER") ? atoi(getenv("SS_ATT_STAGGER")) : 1;  // developer tuning hook
   constexpr int KMAX = 1024;
   using S = AttSmem<D, KMAX>;
   auto kern = patch_attention_tc_kernel<D, KMAX, POLY>;
@@ -475,7 +482,7 @@ static int launch_attention_var(const void* qkv, const int64_t* order_row, const
   // heads fastest: the H CTAs of a patch run together and share the gathered rows' DRAM sectors through L2
   dim3 grid((unsigned)((size_t)heads * max_patches));
   kern<<<grid, kAttThreads, S::kTotal, stream>>>((const __nv_bfloat16*)qkv, order_row, (const int4*)table, heads,
-                                                 scale * 1.4426950408889634f, (__nv_bfloat16*)out);
+                                                 scale * 1.4426950408889634f, (__nv_bfloat16*)out, stagger);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }

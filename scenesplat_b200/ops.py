@@ -239,7 +239,8 @@ def patch_attention(qkv, order_row, table, patch_size: int, heads: int, scale: f
     tc_ok = qkv.dtype == _BF16 and out.dtype == _BF16 and d in (16, 32, 48) and patch_size <= 1024
     if impl == "tc" and not tc_ok:
         raise L.CudaKernelError("tcgen05 attention needs bf16 in/out, head_dim in {16,32,48}, patch_size <= 1024")
-    meta = dict(flops=4.0 * min(patch_size, n) * c * n, bytes=n * (4.0 * c * qkv.element_size() + 8))
+    meta = dict(flops=4.0 * min(patch_size, n) * c * n, bytes=n * (4.0 * c * qkv.element_size() + 8),
+                exps=float(min(patch_size, n)) * n * heads)
     if impl == "tc" or (impl == "auto" and tc_ok):
         L.call("ss_patch_attention", L.ptr(qkv), L.ptr(order_row), L.ptr(table), table.shape[0], patch_size, heads, d,
                float(scale), L.ptr(out), L.stream(), meta=meta)
