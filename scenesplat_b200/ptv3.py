@@ -297,17 +297,30 @@ class SerializedPooling(PointModule):
         if act_layer is not None:
             self.act = PointSequential(act_layer())
 
-    def forward(self, point: Point):
-        _no_training(self)
+    def pooling_depth_for(self, serialized_depth):
         pooling_depth = (math.ceil(self.stride) - 1).bit_length()
-        if pooling_depth > point.serialized_depth:
-            pooling_depth = 0
-        assert {"serialized_code", "serialized_order", "serialized_inverse", "serialized_depth"}.issubset(point.keys()), \
-            "Run point.serialization() point cloud before SerializedPooling"
+        return 0 if pooling_depth > serialized_depth else pooling_depth
+
+    def pool_indices(self, point, pooling_depth):
+        """ref :384-412: cluster ids, pooled codes / orders / inverses / grid_coord / batch (one host sync: the
+        number of coarse voxels) and the order shuffle (one `torch.randperm` from the CPU generator)."""
         k = point.serialized_code.shape[0]
         perm = torch.randperm(k).tolist() if self.shuffle_orders else list(range(k))
         ix = ops.pool_index(point.serialized_code, point.serialized_order, point.grid_coord, point.batch, pooling_depth,
                             perm)
+        return perm, ix
+
+    def forward(self, point: Point):
+        _no_training(self)
+        pooling_depth = self.pooling_depth_for(point.serialized_depth)
+        assert {"serialized_code", "serialized_order", "serialized_inverse", "serialized_depth"}.issubset(point.keys()), \
+            "Run point.serialization() point cloud before SerializedPooling"
+        plan = point.get("_pool_plan", None)  # index hierarchy built ahead of the feature path (PointTransformerV3.forward)
+        if plan is not None and plan["pooling_depth"] == pooling_depth:
+            perm, ix = plan["perm"], plan["ix"]
+        else:
+            plan = None
+            perm, ix = self.pool_indices(point, pooling_depth)
         order0 = point.serialized_order[0].contiguous()
         bn = _single(self.norm, nn.BatchNorm1d) if getattr(self, "norm", None) is not None else None
         act = getattr(self, "act", None)
@@ -334,6 +347,10 @@ class SerializedPooling(PointModule):
             point_dict["pooling_inverse"] = ix["cluster"]
             point_dict["pooling_parent"] = point
         point = Point(point_dict)
+        if plan is not None:
+            point["_kmap_cache"] = plan["kmap_cache"]
+            if plan.get("child") is not None:
+                point["_pool_plan"] = plan["child"]
         if not fuse:
             if getattr(self, "norm", None) is not None:
                 point = self.norm(point)
@@ -493,10 +510,43 @@ class PointTransformerV3(PointModule):
                                   upcast_attention=upcast_attention, upcast_softmax=upcast_softmax), name=f"block{i}")
                 self.dec.add(module=dec, name=f"dec{s}")
 
+    def plan_indices(self, point):
+        """Builds the whole feature-independent index hierarchy up front: pooled codes / orders / clusters of every
+        encoder level, the 3^3 kernel maps and the pair lists of every level.  These are the only steps of a forward
+        that need a host sync (coarse voxel counts, pair counts); doing them first, on kernels that take well under
+        a millisecond each, leaves the feature path (all the heavy kernels) free of syncs, so the host enqueues
+        ahead of the device instead of draining it 7 times per forward.  The CPU RNG is consumed in the reference's
+        order (serialization, then one randperm per pooling level)."""
+        from .spconv_compat import kernel_map_for
+        if not any(isinstance(m, Block) and m.cpe[0].tensor_core_ok() for m in self.modules()):
+            return
+        kernel_map_for(point, 3, want_pairs=True)
+        level = point
+        holder = point  # Dict that receives the plan of the next pooling
+        for stage in self.enc.children():
+            down = getattr(stage, "down", None)
+            if down is None:
+                continue
+            pooling_depth = down.pooling_depth_for(level.serialized_depth)
+            perm, ix = down.pool_indices(level, pooling_depth)
+            names = level.serialized_order_names
+            child = Dict(grid_coord=ix["grid_coord"], batch=ix["batch"], serialized_code=ix["code"],
+                         serialized_order=ix["order"], serialized_depth=level.serialized_depth - pooling_depth,
+                         serialized_order_names=tuple(names[i] for i in perm))
+            kernel_map_for(child, 3, want_pairs=True)
+            plan = dict(pooling_depth=pooling_depth, perm=perm, ix=ix, kmap_cache=child["_kmap_cache"], child=None)
+            if holder is point:
+                point["_pool_plan"] = plan
+            else:
+                holder["child"] = plan
+            holder = plan
+            level = child
+
     def forward(self, data_dict):
         point = Point(data_dict)
         point.serialization(order=self.order, shuffle_orders=self.shuffle_orders)
         point.sparsify()
+        self.plan_indices(point)
         point = self.embedding(point)
         point = self.enc(point)
         if not self.cls_mode:
