@@ -11,18 +11,19 @@
 // Work items (256-row tile, BN-column slab) are walked slab-fastest, so the slabs of one tile run on
 // neighbouring SMs at the same time and their identical A gathers hit L2.
 //
-// 14 warps:  0-3  epilogue (TMEM -> bf16 -> shared-memory transpose -> 64-byte coalesced global stores)
-//            4-11 A producers: 16-byte cp.async gathers into 128B-swizzled K-major tiles, published per thread with
+// 18 warps:  0-7  epilogue, one warp per (row quarter, accumulator): TMEM -> bf16 -> shared-memory transpose ->
+//                 64-byte coalesced global stores
+//            8-15 A producers: 16-byte cp.async gathers into 128B-swizzled K-major tiles, published per thread with
 //                 cp.async.mbarrier.arrive.noinc (the arrival fires when the thread's copies have landed; a
 //                 wait_group + fence + arrive chain was measured to serialise MMA k behind MMA k-1)
-//            12   W producer (TMA, one lane)       13   MMA issuer (tcgen05.mma M128 x N=BN x K16, 8 per stage)
+//            16   W producer (TMA, one lane)       17   MMA issuer (tcgen05.mma M128 x N=BN x K16, 8 per stage)
 // The producers run ahead into the next work item while the epilogue drains the accumulators.
 #include "tc_common.cuh"
 #include "../../include/scenesplat_b200.h"
 
 namespace ss {
 
-constexpr int kG2Threads = 448;
+constexpr int kG2Threads = 576;
 constexpr int kG2TileM = 256;
 constexpr int kG2BK = 64;  // bf16 elements per K chunk = one 128-byte swizzle row
 
@@ -32,8 +33,8 @@ struct Gemm2Smem {
   static constexpr int kBBytes = BN * kG2BK * 2;
   static constexpr int kStageBytes = 2 * kABytes + kBBytes;
   static constexpr int kOffStage = 0;
-  static constexpr int kOffEpi = STAGES * kStageBytes;  // 4 warps x 2 KB transpose buffers
-  static constexpr int kOffBar = kOffEpi + 4 * 2048;
+  static constexpr int kOffEpi = STAGES * kStageBytes;  // 8 warps x 2 KB transpose buffers
+  static constexpr int kOffBar = kOffEpi + 8 * 2048;
   static constexpr int kTotal = kOffBar + 256 + 1024 /*alignment slack*/;
 };
 
@@ -48,7 +49,7 @@ gather_gemm256_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __rest
   uint64_t* full_bar = (uint64_t*)(smem + S::kOffBar);  // [STAGES] 256 gather threads + 1 TMA expect_tx arrive
   uint64_t* empty_bar = full_bar + STAGES;              // [STAGES] one tcgen05.commit
   uint64_t* acc_full = empty_bar + STAGES;              // accumulators of the item complete
-  uint64_t* acc_empty = acc_full + 1;                   // accumulators drained (128 epilogue threads)
+  uint64_t* acc_empty = acc_full + 1;                   // accumulators drained (256 epilogue threads)
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably uniform
@@ -60,19 +61,19 @@ gather_gemm256_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __rest
       tc::mbar_init(&empty_bar[s], 1);
     }
     tc::mbar_init(acc_full, 1);
-    tc::mbar_init(acc_empty, 128);
+    tc::mbar_init(acc_empty, 256);
     tc::mbar_fence_init();
   }
-  if (warp == 12 && lane == 0) tc::tma_prefetch_desc(&tmap_w);
-  if (warp == 13) tc::tmem_alloc<(2 * BN < 32 ? 32 : 2 * BN)>(tmem_slot);
+  if (warp == 16 && lane == 0) tc::tma_prefetch_desc(&tmap_w);
+  if (warp == 17) tc::tmem_alloc<(2 * BN < 32 ? 32 : 2 * BN)>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 12) {
+  if (warp >= 8 && warp < 16) {
     // ------------------------------------------------------------------ A producers (gather), 256 threads
-    const int tid = threadIdx.x - 128;  // 0..255
+    const int tid = threadIdx.x - 256;  // 0..255
     const int sub = tid >> 3, c = tid & 7;  // 8 lanes cover one 128-byte row segment
     int64_t g = 0;                          // chunks issued so far (all items)
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -98,7 +99,7 @@ gather_gemm256_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __rest
         tc::cp_async_mbar_arrive_noinc(&full_bar[s]);
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == 16) {
     // ------------------------------------------------------------------ W producer (TMA, one lane)
     if (lane == 0) {
       int64_t g = 0;
@@ -115,7 +116,7 @@ gather_gemm256_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __rest
         }
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == 17) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane per op)
     constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN);
     const uint64_t d_base = tc::umma_desc_sw128(0);
@@ -143,18 +144,18 @@ gather_gemm256_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __rest
       tc::umma_commit_elect(acc_full);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 0..3
+    // ------------------------------------------------------------------ epilogue warps 0..7: (quarter, accumulator)
     uint8_t* stg = smem + S::kOffEpi + warp * 2048;  // [32 rows][64 B], 16-byte chunks XOR-swizzled by (row >> 1) & 3
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int it = 0;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int64_t tile = item / n_slabs;
       const int n0 = (int)(item - tile * n_slabs) * BN;
       tc::mbar_wait(acc_full, (uint32_t)(it & 1));
       tc::tc_fence_after();
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        __nv_bfloat16* obase = prod + ((size_t)tile * kG2TileM + half * 128 + warp * 32) * cout + n0;
+      {
+        __nv_bfloat16* obase = prod + ((size_t)tile * kG2TileM + half * 128 + quarter * 32) * cout + n0;
 #pragma unroll 1
         for (int j = 0; j < BN / 32; ++j) {
           if (n0 + j * 32 >= cout) break;
@@ -186,7 +187,7 @@ gather_gemm256_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __rest
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == 17) {
     tc::tc_fence_after();
     tc::tmem_dealloc<(2 * BN < 32 ? 32 : 2 * BN)>(tmem_base);
   }
