@@ -187,6 +187,26 @@ int ss_lang_head_tc(const void* feat_bf16, const void* text_bf16, int64_t n, int
                     float threshold, int mode, const int64_t* idx, float* max_prob, int64_t* label, float* probs_accum,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Zero-shot evaluation tail: neighbour voting (pointcept/utils/misc.py:17-95: cKDTree k-NN + majority vote) and
+ * the confusion-matrix update (pointcept/engines/hooks/evaluator.py:830-834).  `origin3` is a HOST pointer to the
+ * three floats of the grid origin; everything else is device memory.  Grid: nx*ny*nz cells of edge `cell`. */
+
+/* cell_id[i] = linear cell of reference point i, cell_count[cell]++ (cell_count zero-initialised by the caller). */
+int ss_vote_bin_count(const float* pts_xyz, int64_t m, const float* origin3, float cell, int nx, int ny, int nz,
+                      int32_t* cell_count, int64_t* cell_id, void* stream);
+/* Counting-sort fill: binned[cell_start[cell] + slot] = (x, y, z, label bits); cursor zero-initialised. */
+int ss_vote_bin_fill(const float* pts_xyz, const int32_t* labels, const int64_t* cell_id, int64_t m,
+                     const int64_t* cell_start, int32_t* cursor, void* binned_xyzl, void* stream);
+/* out[q] = majority label of the k nearest reference points of query q (fp64 distances, ties to the smallest
+ * label, no valid label -> ignore_label).  k <= 64. */
+int ss_knn_vote(const void* binned_xyzl, const int64_t* cell_start, const float* origin3, float cell, int nx, int ny,
+                int nz, const float* query_xyz, int64_t nq, int k, int ignore_label, int num_classes, int32_t* out,
+                void* stream);
+/* confusion[gt, pred] += 1, or fn_ignore[gt] += 1 where pred == ignore_index (int64 counters, atomics). */
+int ss_confusion_update(const int64_t* gt, const int64_t* pred, int64_t n, int num_classes, int64_t ignore_index,
+                        int64_t* confusion, int64_t* fn_ignore, void* stream);
+
 /* acc3 = {sum_valid (1 - cos), sum_valid ||pred - target||^2, n_valid} as doubles
  * (pointcept/models/losses/misc.py:247-295).  target_dtype: 0 fp32, 1 bf16, 2 fp16. */
 int ss_cos_l2_loss(const void* pred, int pred_is_bf16, const void* target, int target_dtype, const uint8_t* mask,

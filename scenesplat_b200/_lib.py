@@ -46,6 +46,10 @@ SIGNATURES = {
     "ss_lang_head_tc": (_i, [_vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "ss_cos_l2_loss": (_i, [_vp, _i, _vp, _i, _vp, _i64, _i, _vp, _vp]),
     "ss_class_half_sums": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "ss_vote_bin_count": (_i, [_vp, _i64, _vp, _f, _i, _i, _i, _vp, _vp, _vp]),
+    "ss_vote_bin_fill": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ss_knn_vote": (_i, [_vp, _vp, _vp, _f, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp]),
+    "ss_confusion_update": (_i, [_vp, _vp, _i64, _i, _i64, _vp, _vp, _vp]),
     "ss_version": (C.c_char_p, []),
     "ss_launch_count": (C.c_uint64, []),
 }
@@ -104,6 +108,11 @@ def stream():
 
 def int_array(vals):
     return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def float_array(vals):
+    """Small HOST array of floats passed by pointer (e.g. a grid origin)."""
+    return C.cast((C.c_float * len(vals))(*[float(v) for v in vals]), C.c_void_p)
 
 
 # Optional per-call device timing (bench.py): name -> list of (start_event, end_event, meta).

@@ -240,3 +240,39 @@ def test_patch_table_vs_golden(golden):
         np.testing.assert_array_equal(np.array(seq_pad), pad)
         np.testing.assert_array_equal(seq_unpad, unpad)
         np.testing.assert_array_equal(np.cumsum([0] + [r[3] - r[2] for r in rows]), cu)
+
+
+@pytest.mark.parametrize("n,k,with_mask,with_query", [(20000, 25, True, False), (5000, 25, False, True), (300, 7, True, True),
+                                                      (40, 25, False, False)])
+def test_neighbor_voting_and_confusion(n, k, with_mask, with_query):
+    """GPU k-NN majority vote (csrc/voting.cu) vs scipy cKDTree + numpy vote (oracle/voting.py, restating
+    pointcept/utils/misc.py:17-95): bit-exact labels (fp64 distances on both sides; real-valued synthetic coordinates
+    have no ties at the k-th neighbour).  Confusion-matrix update vs the reference's per-point loop: bit-exact."""
+    import scenesplat_b200 as S
+    from oracle import voting as ovote
+    from scenesplat_b200 import synthetic
+    rng = np.random.default_rng(n + k)
+    coords = synthetic.room(n, L=4.0, H=2.5, seed=3)
+    num_classes, ignore = 20, -1
+    # spatially coherent labels with noise, some ignored
+    pred = ((coords[:, 0] * 1.7 + coords[:, 1] * 2.3).astype(np.int64) % num_classes)
+    noise = rng.random(n) < 0.3
+    pred[noise] = rng.integers(0, num_classes, noise.sum())
+    pred[rng.random(n) < 0.1] = ignore
+    mask = (rng.random(n) < 0.8) if with_mask else None
+    query = (coords[rng.integers(0, n, n // 2)] + rng.normal(0, 0.05, (n // 2, 3))).astype(np.float32) if with_query else None
+    if with_query:
+        query[:5] += 30.0  # far outside the grid
+    want = ovote.neighbor_voting(coords, pred, min(k, int(mask.sum()) if mask is not None else n), ignore, num_classes, mask, query)
+    got = S.neighbor_voting(dev(coords), dev(pred), k, ignore, num_classes,
+                            dev(mask) if mask is not None else None, dev(query) if query is not None else None)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # confusion matrix
+    gt = rng.integers(0, num_classes, want.shape[0])
+    conf, fn = np.zeros((num_classes, num_classes), np.int64), np.zeros(num_classes, np.int64)
+    ovote.confusion_update(gt, want, num_classes, ignore, conf, fn)
+    conf_d = torch.zeros((num_classes, num_classes), dtype=torch.int64, device="cuda")
+    fn_d = torch.zeros(num_classes, dtype=torch.int64, device="cuda")
+    S.confusion_update(dev(gt), got, num_classes, ignore, conf_d, fn_d)
+    np.testing.assert_array_equal(conf_d.cpu().numpy(), conf)
+    np.testing.assert_array_equal(fn_d.cpu().numpy(), fn)

@@ -171,3 +171,18 @@ def test_ptv3_small_matches_reference(golden):
     ref = g["out_feat"]
     err = np.abs(out.numpy() - ref).max()
     assert err < 2e-4 * max(1.0, np.abs(ref).max()), err
+
+
+def test_voting_oracle_small_cases():
+    """oracle/voting.py against hand-computed cases (reference semantics: pointcept/utils/misc.py:17-95)."""
+    from oracle import voting as ovote
+    nl = np.array([[1, 1, 2, -1], [3, 2, 2, 3], [-1, -1, -1, -1], [7, 0, 0, 7]])
+    out = ovote.majority_vote(nl, -1, 5)
+    assert out.tolist() == [1, 2, -1, 0]  # tie 2 vs 3 -> smallest; all ignored -> ignore; label 7 >= num_classes skipped
+    coords = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [5, 5, 5], [5, 5, 6]], dtype=np.float32)
+    pred = np.array([0, 0, 1, 2, 2])
+    got = ovote.neighbor_voting(coords, pred, 3, -1, 3)
+    assert got.tolist() == [0, 0, 0, 2, 2]
+    conf, fn = np.zeros((3, 3), np.int64), np.zeros(3, np.int64)
+    ovote.confusion_update(np.array([0, 1, 2, 2]), np.array([0, -1, 2, 1]), 3, -1, conf, fn)
+    assert conf.tolist() == [[1, 0, 0], [0, 0, 0], [0, 1, 1]] and fn.tolist() == [0, 1, 0]
