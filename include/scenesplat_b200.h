@@ -188,6 +188,14 @@ int ss_lang_head_tc(const void* feat_bf16, const void* text_bf16, int64_t n, int
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SphereCrop (pointcept/datasets/transform.py:1419-1535, modes "random" / "center"): order[j] = index of the j-th
+ * nearest point to `center3` (HOST pointer, 3 floats), distances in numpy's fp32 arithmetic, ties by ascending
+ * index; dist_bits_sorted[j] = bit pattern of that squared distance (low 32 bits). */
+size_t ss_sphere_crop_workspace_bytes(int64_t n);
+int ss_sphere_crop_order(const float* coord, int64_t n, const float* center3, int64_t* order, uint64_t* dist_bits_sorted,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Zero-shot evaluation tail: neighbour voting (pointcept/utils/misc.py:17-95: cKDTree k-NN + majority vote) and
  * the confusion-matrix update (pointcept/engines/hooks/evaluator.py:830-834).  `origin3` is a HOST pointer to the
  * three floats of the grid origin; everything else is device memory.  Grid: nx*ny*nz cells of edge `cell`. */

@@ -253,7 +253,7 @@ def load_reference():
         encode=ser.encode, Point=structure.Point, ptv3=ptv3,
         PointTransformerV3=ptv3.PointTransformerV3, SerializedPooling=ptv3.SerializedPooling,
         SerializedAttention=ptv3.SerializedAttention, Block=ptv3.Block,
-        losses=losses, Criteria=lb.Criteria, GridSample=transform.GridSample,
+        losses=losses, Criteria=lb.Criteria, GridSample=transform.GridSample, SphereCrop=transform.SphereCrop,
         collate_fn=dutils.collate_fn, SubMConv3d=_SubMConv3d, SparseConvTensor=_SparseConvTensor,
         kernel_map_dense=_kernel_map_dense,
     )

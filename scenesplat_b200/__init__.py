@@ -10,7 +10,7 @@ from .ptv3 import (Block, Embedding, MLP, PointTransformerV3, SerializedAttentio
                    SerializedUnpooling)
 from .lang import (AggregatedContrastiveLoss, CosineSimilarity, Criteria, L2Loss, LangPretrainer,  # noqa: F401
                    zero_shot_accumulate, zero_shot_labels)
-from .transform import GridSample  # noqa: F401
+from .transform import GridSample, SphereCrop  # noqa: F401
 from .voting import confusion_update, neighbor_voting  # noqa: F401
 from .spconv_compat import SparseConvTensor, SubMConv3d  # noqa: F401
 

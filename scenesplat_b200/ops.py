@@ -99,6 +99,19 @@ def gather_rows(src, idx):
     return out
 
 
+def sphere_crop_order(coord, center):
+    """order [n] int64: indices by ascending squared distance to `center` (3 floats on the host), numpy fp32 arithmetic,
+    ties by ascending index (transform.py:1493-1499)."""
+    coord = coord.contiguous()
+    n = coord.shape[0]
+    order = torch.empty(n, dtype=torch.int64, device=coord.device)
+    dist = torch.empty(n, dtype=torch.int64, device=coord.device)
+    ws = L.workspace(L.load().ss_sphere_crop_workspace_bytes(n), coord.device)
+    L.call("ss_sphere_crop_order", L.ptr(coord), n, L.float_array([float(c) for c in center]), L.ptr(order), L.ptr(dist),
+           L.ptr(ws), ws.numel(), L.stream())
+    return order
+
+
 # ------------------------------------------------------------------------------------------- pooling
 def pool_index(code, order, grid_coord, batch, pooling_depth: int, src_row):
     """-> dict(cluster, seg_start, head, m, code, order, inverse, grid_coord, batch) (children sliced to m)."""

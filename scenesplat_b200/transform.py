@@ -90,3 +90,40 @@ class GridSample(object):
                     part[key] = data_dict[key]
             parts.append(part)
         return parts
+
+
+@TRANSFORMS.register_module()
+class SphereCrop(object):
+    """Drop-in for pointcept/datasets/transform.py:1419-1535 (modes "random" and "center"; "all" is the test-time
+    multi-crop generator and is not built).  The distance ranking runs on the GPU (csrc/crop.cu), every per-point
+    array of the dict is gathered on the device.  The random centre index is drawn from numpy's global RNG exactly
+    like the reference (`np.random.randint(N)`)."""
+
+    # every key the reference crops (transform.py:1500-1534), plus `index` if present
+    KEYS = ("coord", "origin_coord", "grid_coord", "color", "quat", "scale", "opacity", "normal", "lang_feat",
+            "valid_feat_mask", "segment", "instance", "displacement", "strength")
+
+    def __init__(self, point_max=80000, sample_rate=None, mode="random", device="cuda"):
+        assert mode in ["random", "center", "all"]
+        if mode == "all":
+            raise NotImplementedError("SphereCrop(mode='all') (test-time multi-crop) is not built")
+        self.point_max, self.sample_rate, self.mode, self.device = point_max, sample_rate, mode, device
+
+    def __call__(self, data_dict):
+        assert "coord" in data_dict.keys()
+        n = data_dict["coord"].shape[0]
+        point_max = int(self.sample_rate * n) if self.sample_rate is not None else self.point_max
+        if n <= point_max:
+            return data_dict
+        as_numpy = isinstance(data_dict["coord"], np.ndarray)
+        to_dev = lambda v: (torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v).to(self.device)
+        coord = to_dev(data_dict["coord"]).float().contiguous()
+        ci = np.random.randint(n) if self.mode == "random" else n // 2
+        order = ops.sphere_crop_order(coord, coord[ci].cpu())
+        idx_crop = order[:point_max].contiguous()
+        for k in self.KEYS:
+            if k in data_dict.keys():
+                v = data_dict[k]
+                g = ops.gather_rows(to_dev(v), idx_crop)
+                data_dict[k] = g.cpu().numpy() if as_numpy else g
+        return data_dict

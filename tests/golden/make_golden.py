@@ -233,8 +233,31 @@ def gen_ptv3_small(ref):
     save("ptv3_small.npz", **arrs)
 
 
+def gen_spherecrop(ref):
+    """SphereCrop (transform.py:1419-1535), modes center and random, under a fixed numpy seed."""
+    out = {}
+    d = synthetic.chunk(30000, L=4.0, H=2.5, seed=11)
+    coord = d["coord"]
+    seg = (np.arange(coord.shape[0]) % 37).astype(np.int64)
+    out["coord_in"] = coord
+    out["segment_in"] = seg
+    for mode in ("center", "random"):
+        np.random.seed(21)
+        sc = ref.SphereCrop(point_max=7000, mode=mode)
+        res = sc(dict(coord=coord.copy(), segment=seg.copy(), color=d["color"].copy()))
+        out[f"{mode}_coord"] = res["coord"]
+        out[f"{mode}_segment"] = res["segment"]
+        out[f"{mode}_color"] = res["color"]
+    np.random.seed(22)
+    sc = ref.SphereCrop(sample_rate=0.25, mode="random")
+    res = sc(dict(coord=coord.copy(), segment=seg.copy()))
+    out["rate_coord"] = res["coord"]
+    out["rate_segment"] = res["segment"]
+    save("spherecrop.npz", **out)
+
+
 if __name__ == "__main__":
     ref = load_reference()
-    which = sys.argv[1:] or ["serialization", "gridsample", "patch_table", "pooling", "losses", "ptv3_small"]
+    which = sys.argv[1:] or ["serialization", "gridsample", "patch_table", "pooling", "losses", "ptv3_small", "spherecrop"]
     for w in which:
         globals()["gen_" + w](ref)

@@ -276,3 +276,48 @@ def test_neighbor_voting_and_confusion(n, k, with_mask, with_query):
     S.confusion_update(dev(gt), got, num_classes, ignore, conf_d, fn_d)
     np.testing.assert_array_equal(conf_d.cpu().numpy(), conf)
     np.testing.assert_array_equal(fn_d.cpu().numpy(), fn)
+
+
+def test_sphere_crop_golden(golden):
+    """GPU SphereCrop vs the reference's own output (tests/golden/spherecrop.npz, generated from the unmodified
+    reference under fixed numpy seeds): the same rows at the same (ascending, bit-identical fp32) distances.  Rows at
+    EXACTLY equal distance may be permuted (numpy's argsort is an unstable introsort, the GPU sort breaks ties by
+    index), so both sides are canonicalised inside tie groups before the bit-exact comparison."""
+    import scenesplat_b200 as S
+    g = golden("spherecrop.npz")
+    from scenesplat_b200 import synthetic
+    color = synthetic.chunk(30000, L=4.0, H=2.5, seed=11)["color"]
+
+    def canon(res, center):
+        d = np.sum(np.square(res["coord"] - center), 1)
+        assert np.all(np.diff(d) >= 0)  # ascending distance
+        c = res["coord"]
+        perm = np.lexsort((c[:, 2], c[:, 1], c[:, 0], d))
+        return d, {k: v[perm] for k, v in res.items()}
+
+    n = g["coord_in"].shape[0]
+    for mode in ("center", "random"):
+        np.random.seed(21)
+        ci = np.random.randint(n) if mode == "random" else n // 2
+        center = g["coord_in"][ci]
+        np.random.seed(21)
+        sc = S.SphereCrop(point_max=7000, mode=mode)
+        res = sc(dict(coord=g["coord_in"].copy(), segment=g["segment_in"].copy(), color=color.copy()))
+        want = dict(coord=g[f"{mode}_coord"], segment=g[f"{mode}_segment"], color=g[f"{mode}_color"])
+        d_got, got_c = canon(res, center)
+        d_want, want_c = canon(want, center)
+        np.testing.assert_array_equal(d_got, d_want)
+        for k in want:
+            np.testing.assert_array_equal(got_c[k], want_c[k])
+    np.random.seed(22)
+    ci = np.random.randint(n)
+    np.random.seed(22)
+    res = S.SphereCrop(sample_rate=0.25, mode="random")(dict(coord=g["coord_in"].copy(), segment=g["segment_in"].copy()))
+    d_got, got_c = canon(res, g["coord_in"][ci])
+    d_want, want_c = canon(dict(coord=g["rate_coord"], segment=g["rate_segment"]), g["coord_in"][ci])
+    np.testing.assert_array_equal(d_got, d_want)
+    np.testing.assert_array_equal(got_c["coord"], want_c["coord"])
+    np.testing.assert_array_equal(got_c["segment"], want_c["segment"])
+    # torch tensors in -> torch tensors (on the GPU) out; fewer points than point_max -> untouched
+    d = dict(coord=dev(g["coord_in"][:100]))
+    assert S.SphereCrop(point_max=1000)(d)["coord"].shape[0] == 100
