@@ -363,6 +363,15 @@ def main():
                             traffic=None, peak_source=pk["src"], share_of_step=r["ms"] / ms,
                             calls_per_step=r["calls"] / args.steps)
     own_ms = sum(r["ms"] for r in own.values()) / prof_steps
+    # the second half of BASELINE.json's metric: serialize + pool achieved HBM GB/s (algorithmic bytes of SURVEY 8d:
+    # 128 B / Gaussian for the 4-order serialization, N (28 + C e) + M (148 + 4 C) for a pooling level)
+    sp = [table[k] for k in ("ss_serialize", "ss_pool_index", "ss_segment_reduce") if k in table]
+    serialize_pool = None
+    if sp:
+        sp_bytes, sp_ms = sum(r["bytes"] for r in sp), sum(r["ms"] for r in sp)
+        serialize_pool = dict(gbs=sp_bytes / (sp_ms * 1e-3) / 1e9, frac_of_hbm=sp_bytes / (sp_ms * 1e-3) / 1e9 / pk["hbm"],
+                              ms_per_step=sp_ms / prof_steps, bytes_per_step=sp_bytes / prof_steps,
+                              note="launch-latency bound at 300 k Gaussians: 11 launches move 70 MB")
 
     if rank == 0:
         cpu = None
@@ -389,7 +398,7 @@ def main():
                      for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])},
             kernels_note="per-call CUDA-event times from a separate instrumented pass; the roofline kernel is timed "
                          "inside the timed region itself",
-            roofline=roofline, cpu_baseline=cpu, clocks=clocks,
+            roofline=roofline, serialize_pool_hbm=serialize_pool, cpu_baseline=cpu, clocks=clocks,
         )
         print(json.dumps(line), flush=True)
     if world > 1:

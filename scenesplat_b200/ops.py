@@ -113,6 +113,9 @@ def sphere_crop_order(coord, center):
 
 
 # ------------------------------------------------------------------------------------------- pooling
+_POOL_META = dict(bytes=0.0)
+
+
 def pool_index(code, order, grid_coord, batch, pooling_depth: int, src_row):
     """-> dict(cluster, seg_start, head, m, code, order, inverse, grid_coord, batch) (children sliced to m)."""
     k, n = code.shape
@@ -131,8 +134,11 @@ def pool_index(code, order, grid_coord, batch, pooling_depth: int, src_row):
     L.call("ss_pool_index", L.ptr(code.contiguous()), L.ptr(order.contiguous()), L.ptr(gc),
            L.ptr(batch.contiguous() if batch is not None else None), n, k, pooling_depth, L.int_array(src_row), n,
            L.ptr(cluster), L.ptr(seg_start), L.ptr(head), L.ptr(m_dev), L.ptr(ccode), L.ptr(corder), L.ptr(cinv),
-           L.ptr(cgc), L.ptr(cb), L.ptr(ws), ws.numel(), L.stream())
+           L.ptr(cgc), L.ptr(cb), L.ptr(ws), ws.numel(), L.stream(), meta=_POOL_META)
     m = int(m_dev.item())
+    if L.PROFILE is not None and L.PROFILE.get("ss_pool_index"):  # algorithmic bytes need m: N*28 + M*148
+        rec = L.PROFILE["ss_pool_index"][-1]
+        L.PROFILE["ss_pool_index"][-1] = (rec[0], rec[1], dict(bytes=n * 28.0 + m * 148.0))
     return dict(cluster=cluster, seg_start=seg_start[: m + 1], head=head[:m], m=m,
                 code=ccode[:, :m].contiguous(), order=corder[:, :m].contiguous(), inverse=cinv[:, :m].contiguous(),
                 grid_coord=cgc[:m] if cgc is not None else None, batch=cb[:m] if cb is not None else None)

@@ -55,15 +55,25 @@ LANG_SHAPED = dict(
 )
 
 
-def test_lang_shaped_vs_oracle():
+@pytest.mark.parametrize("batching", ["two_items", "eight_ragged_items"])
+def test_lang_shaped_vs_oracle(batching):
+    """Whole forward at the lang config's channel / head / patch shapes against the CPU oracle.  "eight_ragged_items"
+    is the batch layout of a training step (BASELINE configs[3]: 8 chunks per batch) with items of very different
+    sizes: shorter than one 128-row tile, shorter than the patch size (one ragged sequence) and longer than one
+    patch (the last patch borrows keys from its left neighbour, ref :114-170)."""
     import scenesplat_b200 as S
-    d = synthetic.chunk(9000, L=2.4, H=1.6, seed=33)
+    d = synthetic.chunk(9000 if batching == "two_items" else 14000, L=2.4, H=1.6, seed=33)
     res = ogs.grid_sample_train(d["coord"], 0.02)
     idx = res["idx_unique"]
     feat = synthetic.feat_from({k: v[idx] for k, v in d.items()})
     coord = d["coord"][idx]
     n = coord.shape[0]
-    offset = np.array([n // 4, n], dtype=np.int64)
+    if batching == "two_items":
+        offset = np.array([n // 4, n], dtype=np.int64)
+    else:
+        sizes = [40, 130, 700, 1024, 1500, 2300, 3000]
+        assert n > sum(sizes) + 1100
+        offset = np.cumsum(sizes + [n - sum(sizes)]).astype(np.int64)
     torch.manual_seed(0)
     model = S.PointTransformerV3(**LANG_SHAPED).eval()
     with torch.no_grad():
