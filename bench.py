@@ -45,7 +45,7 @@ N_RAW = 360000          # -> 299,277 voxels after GridSample(0.02) on the synthe
 CPU_SAMPLE_RAW = 120000  # bounded CPU sample: a ~100k-voxel sub-chunk of the same generator (10-30 s of CPU work)
 METRIC = "gaussians_per_s_ptv3_fwd"
 MUFU_PEAK_TEXP = 4.63                     # measured ex2 throughput of one B200, T/s (tools/micro/mufu.cu)
-ATTENTION_DRAM_BYTES_PER_LAUNCH = 290.4e6  # ncu dram read+write, mean of the 18 launches of a step (profiles/r1_launches_v2.md)
+ATTENTION_DRAM_BYTES_PER_LAUNCH = 290.4e6  # ncu dram read+write, mean of the 18 launches of a step (profiles/r1_launches_v3.md)
 UNIT = "Gaussians/s"
 
 
@@ -371,7 +371,7 @@ def main():
         sp_bytes, sp_ms = sum(r["bytes"] for r in sp), sum(r["ms"] for r in sp)
         serialize_pool = dict(gbs=sp_bytes / (sp_ms * 1e-3) / 1e9, frac_of_hbm=sp_bytes / (sp_ms * 1e-3) / 1e9 / pk["hbm"],
                               ms_per_step=sp_ms / prof_steps, bytes_per_step=sp_bytes / prof_steps,
-                              note="launch-latency bound at 300 k Gaussians: 11 launches move 70 MB")
+                              note="small launches (serialization 38 MB, three pooling levels): latency-bound at 300 k Gaussians")
 
     if rank == 0:
         cpu = None
