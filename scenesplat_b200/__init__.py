@@ -8,8 +8,8 @@ from .registry import LOSSES, MODELS, TRANSFORMS, build_model, register_into_poi
 from .structure import Point  # noqa: F401
 from .ptv3 import (Block, Embedding, MLP, PointTransformerV3, SerializedAttention, SerializedPooling,  # noqa: F401
                    SerializedUnpooling)
-from .lang import (AggregatedContrastiveLoss, CosineSimilarity, Criteria, L2Loss, LangPretrainer,  # noqa: F401
-                   zero_shot_accumulate, zero_shot_labels)
+from .lang import (AggregatedContrastiveLoss, ChunkPipeline, CosineSimilarity, Criteria, L2Loss,  # noqa: F401
+                   LangPretrainer, zero_shot_accumulate, zero_shot_labels)
 from .transform import GridSample, SphereCrop  # noqa: F401
 from .voting import confusion_update, neighbor_voting  # noqa: F401
 from .spconv_compat import SparseConvTensor, SubMConv3d  # noqa: F401

@@ -135,6 +135,16 @@ class LangPretrainer(nn.Module):
         point_feat["feat"] = ops.l2_normalize(point_feat["feat"], eps=1e-12)  # F.normalize(p=2, dim=1), default.py:98
         return point_feat
 
+    def prepare(self, input_dict):
+        """Index phase (serialization, pooling levels, kernel maps; all host syncs) -> prepared Point."""
+        return self.backbone.prepare(Point(input_dict))
+
+    def features_prepared(self, point):
+        """Feature phase on a prepared Point (eval): L2-normalised point features, no host sync."""
+        point_feat = self.backbone.run(point)
+        point_feat["feat"] = ops.l2_normalize(point_feat["feat"], eps=1e-12)
+        return point_feat
+
     def forward(self, input_dict, chunk_size=None):
         if chunk_size is not None and chunk_size > 0 and input_dict["coord"].shape[0] > chunk_size:
             return self._chunked_forward(input_dict, chunk_size)
@@ -178,3 +188,62 @@ def zero_shot_labels(feat, text_embeddings, threshold=0.1, normalize=False):
 def zero_shot_accumulate(pred_probs, feat, text_embeddings, idx_part=None):
     """test.py:335-349: pred[idx_part] += sigmoid(feat @ T^T); fused, logits never materialised."""
     return ops.lang_head_accumulate(feat, text_embeddings, pred_probs, idx_part)
+
+
+class ChunkPipeline(object):
+    """Two-stage software pipeline over a stream of independent chunks (the unit the path shards by: batch items,
+    preprocessing chunks, test fragments; pointcept/models/default.py:134-176, pointcept/engines/test.py:315-349).
+
+    Stage 1 (side stream): host-to-device copy of the chunk (if it comes from pinned host memory) and the index phase
+    (`LangPretrainer.prepare`: serialization, pooling levels, kernel maps, pair lists; the only place with host syncs).
+    Stage 2 (main stream): the feature phase.  While the device runs the heavy kernels of chunk i, the host and
+    a few SMs build the indices of chunk i + 1, so the main stream never drains.  Results are identical to calling
+    the model chunk by chunk (same kernels, same order of the CPU RNG draws).
+
+        pipe = ChunkPipeline(model)
+        for feat in pipe.map(chunks):   # yields the [N_i, 768] feature tensor of every chunk, in order
+            ...
+    """
+
+    def __init__(self, model, device=None):
+        self.model = model
+        self.device = device or next(model.parameters()).device
+        self.side = torch.cuda.Stream(device=self.device)
+        self._keep = []  # prepared points stay referenced until the main stream has consumed them
+
+    def _stage1(self, chunk):
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.side):
+            d = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in chunk.items()}
+            point = self.model.prepare(d)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        return point, ev, main
+
+    def map(self, chunks):
+        it = iter(chunks)
+        try:
+            nxt = self._stage1(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            point, ev, main = nxt
+            main.wait_event(ev)
+            with torch.no_grad():
+                out = self.model.features_prepared(point)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._keep.append((point, done))
+            try:
+                nxt = self._stage1(next(it))  # overlaps the feature phase just enqueued
+            except StopIteration:
+                nxt = None
+            while len(self._keep) > 2:  # memory made on the side stream is released only after its last use
+                _, old = self._keep.pop(0)
+                old.synchronize()
+            yield out["feat"]
+
+    def flush(self):
+        for _, ev in self._keep:
+            ev.synchronize()
+        self._keep.clear()

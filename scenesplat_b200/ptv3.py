@@ -542,13 +542,23 @@ class PointTransformerV3(PointModule):
             holder = plan
             level = child
 
-    def forward(self, data_dict):
+    def prepare(self, data_dict):
+        """Index phase of a forward: serialization + the whole feature-independent index hierarchy (all the host
+        syncs of a forward live here).  May run on a side stream while the feature phase of the previous chunk
+        occupies the device (`ChunkPipeline`)."""
         point = Point(data_dict)
         point.serialization(order=self.order, shuffle_orders=self.shuffle_orders)
         point.sparsify()
         self.plan_indices(point)
+        return point
+
+    def run(self, point):
+        """Feature phase of a forward on a prepared Point: no host sync."""
         point = self.embedding(point)
         point = self.enc(point)
         if not self.cls_mode:
             point = self.dec(point)
         return point
+
+    def forward(self, data_dict):
+        return self.run(self.prepare(data_dict))

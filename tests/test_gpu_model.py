@@ -123,3 +123,37 @@ def test_lang_pretrainer_and_zero_shot(golden):
     probs = torch.sigmoid(full.float() @ text.t())
     np.testing.assert_allclose(mx.cpu().numpy(), probs.max(1).values.cpu().numpy(), atol=1e-3)  # bf16 operands
     assert (lab == probs.argmax(1)).float().mean().item() > 0.97
+
+
+def test_chunk_pipeline_matches_sequential(golden):
+    """ChunkPipeline (index phase of chunk i+1 on a side stream under the feature phase of chunk i) returns exactly
+    what chunk-by-chunk calls return: same kernels, same order of the CPU RNG draws (shuffle_orders=True)."""
+    import scenesplat_b200 as S
+    from tests.golden.make_golden import SMALL_CFG
+    g = golden("ptv3_small.npz")
+    cfg = dict(SMALL_CFG, type="PT-v3m1", dec_channels=(768, 32, 32), dec_num_head=(16, 2, 2))
+    torch.manual_seed(0)
+    model = S.LangPretrainer(backbone=cfg, criteria=[]).cuda().eval()
+    n = g["coord"].shape[0]
+    chunks = []
+    for a, b in ((0, n), (0, n // 2), (n // 3, n), (n // 2, n // 2 + 300)):
+        chunks.append(dict(coord=torch.from_numpy(g["coord"][a:b]).cuda(), grid_coord=torch.from_numpy(g["grid_coord"][a:b]).cuda(),
+                           feat=torch.from_numpy(g["feat"][a:b]).cuda(), offset=torch.tensor([b - a]).cuda()))
+    torch.manual_seed(5)
+    with torch.no_grad():
+        want = [model(dict(c))["point_feat"]["feat"].clone() for c in chunks]
+    torch.manual_seed(5)
+    pipe = S.ChunkPipeline(model)
+    got = [f.clone() for f in pipe.map([dict(c) for c in chunks])]
+    pipe.flush()
+    torch.cuda.synchronize()
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    # pinned host chunks (the H2D copy is part of stage 1)
+    torch.manual_seed(5)
+    host = [{k: v.cpu().pin_memory() for k, v in c.items()} for c in chunks]
+    got = [f.clone() for f in S.ChunkPipeline(model).map(host)]
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
