@@ -91,10 +91,11 @@ int ss_segment_reduce(const void* src, int src_is_bf16, const int64_t* order, co
                       int act, void* out, int out_is_bf16, void* stream);
 
 /* out[i,:] = f_a(a[i,:]) + f_b(b[cluster[i],:]); f = optional affine + activation.  out_a (nullable)
- * receives f_a(a) alone (what the reference's stale sparse_conv_feat holds after unpooling). */
+ * receives f_a(a) alone (what the reference's stale sparse_conv_feat holds after unpooling).
+ * out_flags: bit 0 = out is bf16 (else fp32), bit 1 = out_a is bf16 even when out is fp32. */
 int ss_unpool_gather_add(const void* a, const void* b, int in_is_bf16, const int64_t* cluster, int64_t n, int channels,
                          const float* scale_a, const float* shift_a, const float* scale_b, const float* shift_b, int act,
-                         void* out, void* out_a, int out_is_bf16, void* stream);
+                         void* out, void* out_a, int out_flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Submanifold convolution (replaces spconv.SubMConv3d, call sites

@@ -194,11 +194,11 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-template <typename TI, typename TO>
+template <typename TI, typename TO, typename TA>
 __global__ void __launch_bounds__(256)
 unpool_vec8_kernel(const TI* __restrict__ a, const TI* __restrict__ b, const int64_t* __restrict__ cluster, int64_t n,
                    int C, const float* __restrict__ sa, const float* __restrict__ ta, const float* __restrict__ sb,
-                   const float* __restrict__ tb, int act, TO* __restrict__ out, TO* __restrict__ out_a) {
+                   const float* __restrict__ tb, int act, TO* __restrict__ out, TA* __restrict__ out_a) {
   const int c8 = C >> 3;
   const int64_t total = n * c8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -231,7 +231,7 @@ unpool_vec8_kernel(const TI* __restrict__ a, const TI* __restrict__ b, const int
 #pragma unroll
     for (int u = 0; u < 8; ++u) o[u] = va[u] + vb[u];
     store8<TO>(out + (size_t)r * C + c, o);
-    if (out_a) store8<TO>(out_a + (size_t)r * C + c, va);
+    if (out_a) store8<TA>(out_a + (size_t)r * C + c, va);
   }
 }
 
@@ -317,27 +317,36 @@ int ss_segment_reduce(const void* src, int src_is_bf16, const int64_t* order, co
 
 int ss_unpool_gather_add(const void* a, const void* b, int in_is_bf16, const int64_t* cluster, int64_t n, int channels,
                          const float* scale_a, const float* shift_a, const float* scale_b, const float* shift_b, int act,
-                         void* out, void* out_a, int out_is_bf16, void* stream_) {
+                         void* out, void* out_a, int out_flags, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int out_is_bf16 = out_flags & 1;
   if (n < 0 || channels < 1 || (scale_a && !shift_a) || (scale_b && !shift_b)) return SS_BAD_ARGS;
   if (n == 0) return SS_OK;
   if (!a || !b || !cluster || !out) return SS_BAD_ARGS;
   const bool vec = channels % 8 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out | (uintptr_t)out_a |
                                            (uintptr_t)scale_a | (uintptr_t)shift_a | (uintptr_t)scale_b |
                                            (uintptr_t)shift_b) % 16 == 0);
+  const bool a_bf16 = (out_flags & 2) != 0 || out_is_bf16;  // bit 1: out_a in bf16 even when out is fp32
   if (vec) {
     const int vblocks = (int)ss::imin64(ss::ceil_div64(n * (channels / 8), 256), 16 * ss::kNumSMs);
-#define SS_UNPOOL_V_(TI, TO)                                                                                         \
-  ss::unpool_vec8_kernel<TI, TO><<<vblocks, 256, 0, stream>>>((const TI*)a, (const TI*)b, cluster, n, channels, scale_a, \
-                                                              shift_a, scale_b, shift_b, act, (TO*)out, (TO*)out_a)
-    if (in_is_bf16 && out_is_bf16) SS_UNPOOL_V_(__nv_bfloat16, __nv_bfloat16);
-    else if (in_is_bf16) SS_UNPOOL_V_(__nv_bfloat16, float);
-    else if (out_is_bf16) SS_UNPOOL_V_(float, __nv_bfloat16);
-    else SS_UNPOOL_V_(float, float);
+#define SS_UNPOOL_V_(TI, TO, TA)                                                                                          \
+  ss::unpool_vec8_kernel<TI, TO, TA><<<vblocks, 256, 0, stream>>>((const TI*)a, (const TI*)b, cluster, n, channels, scale_a, \
+                                                                  shift_a, scale_b, shift_b, act, (TO*)out, (TA*)out_a)
+#define SS_UNPOOL_VA_(TI, TO)                                   \
+  do {                                                          \
+    if (a_bf16) SS_UNPOOL_V_(TI, TO, __nv_bfloat16);            \
+    else SS_UNPOOL_V_(TI, TO, float);                           \
+  } while (0)
+    if (in_is_bf16 && out_is_bf16) SS_UNPOOL_VA_(__nv_bfloat16, __nv_bfloat16);
+    else if (in_is_bf16) SS_UNPOOL_VA_(__nv_bfloat16, float);
+    else if (out_is_bf16) SS_UNPOOL_VA_(float, __nv_bfloat16);
+    else SS_UNPOOL_VA_(float, float);
+#undef SS_UNPOOL_VA_
 #undef SS_UNPOOL_V_
     SS_CHECK_LAUNCH();
     return SS_OK;
   }
+  if (a_bf16 != (out_is_bf16 != 0)) return SS_BAD_ARGS;  // the scalar fallback writes out and out_a in one dtype
   const int blocks = (int)ss::imin64(ss::ceil_div64(n * channels, 256), 16 * ss::kNumSMs);
   if (in_is_bf16 && out_is_bf16)
     ss::unpool_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, stream>>>(

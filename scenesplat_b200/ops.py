@@ -159,14 +159,16 @@ def segment_reduce(src, order_row, seg_start, reduce="mean", scale=None, shift=N
 
 
 def unpool_gather_add(a, b, cluster, scale_a=None, shift_a=None, scale_b=None, shift_b=None, act=0, out_dtype=None,
-                      want_a=False):
+                      want_a=False, a_dtype=None):
     a, b = a.contiguous(), b.contiguous()
     n, c = a.shape
     od = out_dtype or a.dtype
+    ad = a_dtype or od
     out = torch.empty((n, c), dtype=od, device=a.device)
-    out_a = torch.empty((n, c), dtype=od, device=a.device) if want_a else None
+    out_a = torch.empty((n, c), dtype=ad, device=a.device) if want_a else None
+    flags = int(od == _BF16) | (2 if (want_a and ad == _BF16) else 0)
     L.call("ss_unpool_gather_add", L.ptr(a), L.ptr(b), _isbf(a), L.ptr(cluster), n, c, L.ptr(scale_a), L.ptr(shift_a),
-           L.ptr(scale_b), L.ptr(shift_b), act, L.ptr(out), L.ptr(out_a), _isbf(out), L.stream())
+           L.ptr(scale_b), L.ptr(shift_b), act, L.ptr(out), L.ptr(out_a), flags, L.stream())
     return out, out_a
 
 

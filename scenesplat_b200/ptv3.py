@@ -398,8 +398,10 @@ class SerializedUnpooling(PointModule):
         s = linear_bf16(lin_s, _bf16_of(parent, parent.feat))
         sc_s, sh_s = bn_fold(bn_s) if bn_s is not None else (None, None)
         sc_p, sh_p = bn_fold(bn_p) if bn_p is not None else (None, None)
+        # `skip` is only ever read as the bf16 operand of the next block's xCPE conv: written as bf16 directly
+        # (fp32 in the reference; saves the fp32 write and a separate cast pass over N x C)
         out, skip = ops.unpool_gather_add(s, a, inverse, sc_s, sh_s, sc_p, sh_p, 1 if act_s is not None else 0,
-                                          out_dtype=torch.float32, want_a=True)
+                                          out_dtype=torch.float32, want_a=True, a_dtype=BF16)
         parent.feat = out
         # ref :478 rebinds parent.feat only: sparse_conv_feat keeps the skip projection (oracle/ptv3.py)
         parent.sparse_conv_feat = parent.sparse_conv_feat.replace_feature(skip)
