@@ -25,7 +25,13 @@ from . import serialization as oser
 from . import subm_conv as oconv
 
 
+BN_TRAINING = False  # set by ptv3_forward_autograd(bn_training=True): batch statistics (train mode), momentum 0.01
+
+
 def _bn_eval(x, sd, p, eps=1e-3):
+    if BN_TRAINING:  # nn.BatchNorm1d(eps=1e-3, momentum=0.01).train(): running stats updated on private copies
+        return F.batch_norm(x, sd[p + "running_mean"].clone(), sd[p + "running_var"].clone(), sd[p + "weight"],
+                            sd[p + "bias"], training=True, momentum=0.01, eps=eps)
     return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
                         training=False, eps=eps)
 
@@ -76,7 +82,13 @@ def pooling_forward(pt: PointState, sd, p, perm):
     """ptv3:371-444 (stride 2 -> pooling_depth 1)."""
     ix = opool.pool_index(pt.code, 1, perm)
     proj = _lin(pt.feat, sd, p + "proj.")
-    feat = torch.from_numpy(opool.segment_csr(proj.numpy(), ix["indices"], ix["idx_ptr"], "mean"))
+    if proj.requires_grad:  # differentiable twin of segment_csr(mean) for the gradient oracle
+        cnt = np.diff(ix["idx_ptr"])
+        seg = torch.from_numpy(np.repeat(np.arange(len(cnt)), cnt))
+        feat = torch.zeros(len(cnt), proj.shape[1]).index_add_(0, seg, proj[torch.from_numpy(ix["indices"])])
+        feat = feat / torch.from_numpy(cnt.astype(np.float32))[:, None]
+    else:
+        feat = torch.from_numpy(opool.segment_csr(proj.numpy(), ix["indices"], ix["idx_ptr"], "mean"))
     coord = opool.segment_csr(pt.coord, ix["indices"], ix["idx_ptr"], "mean")
     gc, b = opool.pooled_attrs(pt.grid_coord, pt.batch, ix["head"], 1)
     offset = np.cumsum(np.bincount(b, minlength=len(pt.offset))).astype(np.int64)
@@ -104,8 +116,24 @@ def unpooling_forward(pt: PointState, sd, p):
     return parent
 
 
+def ptv3_forward_autograd(sd, cfg, coord, grid_coord, feat, offset, perms=None, prefix="", bn_training=True):
+    """The same forward with autograd enabled (parameters in `sd` may require grad) and, by default, train-mode
+    BatchNorm: the gradient oracle of tests/test_gpu_train.py (DropPath must be off: it is random)."""
+    global BN_TRAINING
+    old, BN_TRAINING = BN_TRAINING, bn_training
+    try:
+        with torch.enable_grad():
+            return _ptv3_forward(sd, cfg, coord, grid_coord, feat, offset, perms, prefix, None)
+    finally:
+        BN_TRAINING = old
+
+
 @torch.no_grad()
 def ptv3_forward(sd, cfg, coord, grid_coord, feat, offset, perms=None, prefix="", taps=None):
+    return _ptv3_forward(sd, cfg, coord, grid_coord, feat, offset, perms, prefix, taps)
+
+
+def _ptv3_forward(sd, cfg, coord, grid_coord, feat, offset, perms=None, prefix="", taps=None):
     """sd: fp32 state_dict with the reference's keys (optionally under ``prefix``);
     cfg: dict with the PT-v3m1 kwargs; perms: list of row permutations, one per
     ``randperm`` call in forward order (serialization, then each SerializedPooling), or

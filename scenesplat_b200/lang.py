@@ -5,7 +5,8 @@ Drop-in for (reference):
   Criteria / build_criteria      pointcept/models/losses/builder.py:13-36
   CosineSimilarity, L2Loss, AggregatedContrastiveLoss   pointcept/models/losses/misc.py:247-421
   zero-shot head                 pointcept/engines/hooks/evaluator.py:793-800, pointcept/engines/test.py:335-349
-Forward values only (no autograd through the fused kernels yet).
+Inference uses the fused kernels; under autograd (training) the losses switch to torch operators
+(scenesplat_b200/training.py).
 """
 from __future__ import annotations
 
@@ -25,6 +26,10 @@ class CosineSimilarity(nn.Module):
         self.reduction, self.loss_weight = reduction, loss_weight
 
     def forward(self, pred, target, valid_feat_mask, **kwargs):
+        if pred.requires_grad:
+            from . import training
+            assert self.reduction == "mean"
+            return training.cosine_loss(pred, target, valid_feat_mask, self.loss_weight)
         acc = ops.cos_l2_sums(pred, target, valid_feat_mask)
         loss = acc[0]
         if self.reduction == "mean":
@@ -39,6 +44,10 @@ class L2Loss(nn.Module):
         self.reduction, self.loss_weight = reduction, loss_weight
 
     def forward(self, pred, target, valid_feat_mask, **kwargs):
+        if pred.requires_grad:
+            from . import training
+            assert self.reduction == "mean"
+            return training.l2_loss(pred, target, valid_feat_mask, self.loss_weight)
         acc = ops.cos_l2_sums(pred, target, valid_feat_mask)
         loss = acc[1]
         if self.reduction == "mean":
@@ -83,7 +92,11 @@ class AggregatedContrastiveLoss(nn.Module):
         nc = self.max_classes
         if half is None:
             half, _ = self.random_halves(valid, segment, nc)
-        sums, counts = ops.class_half_sums(pred, valid, segment, half, nc)
+        if pred.requires_grad:
+            from . import training
+            sums, counts = training.class_half_sums(pred.float(), valid, segment, half, nc)
+        else:
+            sums, counts = ops.class_half_sums(pred, valid, segment, half, nc)
         per_class = counts.view(nc, 2).sum(1)
         use = (per_class >= 100) & (counts.view(nc, 2).min(1).values > 0)  # losses/misc.py:366-376
         idx = use.nonzero(as_tuple=True)[0]
@@ -132,7 +145,10 @@ class LangPretrainer(nn.Module):
     def _features(self, input_dict):
         point = Point(input_dict)
         point_feat = self.backbone(point)
-        point_feat["feat"] = ops.l2_normalize(point_feat["feat"], eps=1e-12)  # F.normalize(p=2, dim=1), default.py:98
+        if point_feat["feat"].requires_grad:  # training: torch operator under autograd
+            point_feat["feat"] = F.normalize(point_feat["feat"].float(), p=2, dim=1)
+        else:
+            point_feat["feat"] = ops.l2_normalize(point_feat["feat"], eps=1e-12)  # F.normalize(p=2, dim=1), default.py:98
         return point_feat
 
     def prepare(self, input_dict):

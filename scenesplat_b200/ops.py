@@ -212,7 +212,8 @@ def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = None):
     L.call("ss_kmap_pairs", L.ptr(nbr), L.ptr(order_row.contiguous()), n, k, L.ptr(base_dev), p_pad, L.ptr(pair_in),
            L.ptr(ypos), L.ptr(ws), ws.numel(), L.stream())
     return dict(pair_in=pair_in, ypos=ypos, tile_tap=torch.tensor(tile_tap or [0], dtype=torch.int32, device=dev),
-                p_pad=p_pad, pairs=int(sum(int(c) for c in tap_count_host)), tile=tile)
+                p_pad=p_pad, pairs=int(sum(int(c) for c in tap_count_host)), tile=tile, tap_base=list(base),
+                tap_count=[int(c) for c in tap_count_host])
 
 
 def subm_conv_simt(x, nbr, wt, bias=None, scale=None, shift=None, act=0, out_dtype=None):

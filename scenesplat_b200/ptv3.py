@@ -563,4 +563,8 @@ class PointTransformerV3(PointModule):
         return point
 
     def forward(self, data_dict):
+        if torch.is_grad_enabled() and self.training:
+            # training: autograd around the package's kernels (scenesplat_b200/training.py)
+            from . import training
+            return Point(Dict(feat=training.forward_train(self, data_dict)))
         return self.run(self.prepare(data_dict))

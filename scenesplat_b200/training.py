@@ -1,0 +1,335 @@
+"""Training path of PT-v3m1 / LangPretrainer: forward AND backward.
+
+The reference trains with torch autograd around three third-party operators (spconv SubMConv3d, flash-attn varlen,
+torch_scatter segment_csr; pointcept/models/point_transformer_v3/point_transformer_v3m1_base.py).  This module keeps
+that structure: Linear / LayerNorm / BatchNorm(train) / GELU / DropPath / residuals are torch operators under autograd
+(bf16 GEMMs through cuBLASLt, like the reference's AMP linears), and the three third-party operators are replaced by
+`torch.autograd.Function`s over this package's kernels:
+
+  SubMConvFn      forward: tcgen05 gather-GEMM + gather-sum (csrc/conv_gemm2.cu, conv_gemm.cu)
+                  dgrad:   THE SAME kernels on the mirrored taps with transposed weights (the submanifold kernel map is
+                           symmetric: nbr[t][p] = q  <=>  nbr[26-t][q] = p)
+                  wgrad:   per-tap GEMM dY[pair_out]^T X[pair_in] (gathers + cuBLASLt)         [library GEMM, round 2:
+                           gathered-A x gathered-B tcgen05 kernel]
+  StemConvFn      forward: csrc/conv_simt.cu; wgrad per tap (the stem's input needs no gradient)
+  PatchAttentionFn forward: tcgen05 patch attention (csrc/attention_tc.cu)
+                  backward: recomputation with torch's fused SDPA on the gathered patches       [library, round 2:
+                           tcgen05 backward kernel]
+  SegmentMeanFn   forward: csrc/pool.cu segment_reduce; backward: gather / count
+
+Indices (serialization, pooling levels, kernel maps, patch tables) carry no gradient and come from the same
+`PointTransformerV3.prepare` as inference.  Gradients are checked against torch autograd through the CPU oracle
+(tests/test_gpu_train.py).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .spconv_compat import kernel_map_for
+from .structure import Dict, Point
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def _pair_out(pairs):
+    """Output voxel of every product row (inverse of ypos); padding rows point at voxel 0 and are never used."""
+    if "pair_out" not in pairs:
+        ypos = pairs["ypos"]
+        mask = ypos >= 0
+        po = torch.zeros(max(pairs["p_pad"], 1), dtype=torch.long, device=ypos.device)
+        po[ypos[mask].long()] = mask.nonzero()[:, 1]
+        pairs["pair_out"] = po
+    return pairs["pair_out"]
+
+
+class SubMConvFn(torch.autograd.Function):
+    """y[p] = b + sum_t W_t x[nbr[t][p]]  (3^3 submanifold conv, bf16 operands, fp32 accumulate)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pairs, n):
+        cout, cin = weight.shape[0], weight.shape[-1]
+        k3 = weight.numel() // (cout * cin)
+        w = weight.detach().reshape(cout, k3, cin).permute(1, 0, 2).contiguous().to(BF16)  # [k3, cout, cin]
+        y = ops.subm_conv_gemm(x, pairs, w, bias.detach().float() if bias is not None else None, n, out_dtype=BF16)
+        ctx.save_for_backward(x, weight)
+        ctx.pairs, ctx.n, ctx.has_bias = pairs, n, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        pairs, n = ctx.pairs, ctx.n
+        cout, cin = weight.shape[0], weight.shape[-1]
+        k3 = weight.numel() // (cout * cin)
+        dy = dy.contiguous().to(BF16)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dx[q] = sum_t W_t^T dy[p : nbr[t][p] = q] = conv over the mirrored taps with W'_t = W_{k3-1-t}^T
+            wt = weight.detach().reshape(cout, k3, cin).permute(1, 2, 0).flip(0).contiguous().to(BF16)  # [k3, cin, cout]
+            dx = ops.subm_conv_gemm(dy, pairs, wt, None, n, out_dtype=BF16)
+        if ctx.needs_input_grad[1]:
+            pin, pout = pairs["pair_in"].long(), _pair_out(pairs)
+            dw = torch.zeros((k3, cout, cin), dtype=torch.float32, device=x.device)
+            for t, (b0, c) in enumerate(zip(pairs["tap_base"], pairs["tap_count"])):
+                if c > 0:
+                    dw[t] = torch.mm(dy[pout[b0:b0 + c]].t(), x[pin[b0:b0 + c]]).float()
+            dw = dw.permute(1, 0, 2).reshape(weight.shape).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum(0)
+        return dx, dw, db, None, None
+
+
+class StemConvFn(torch.autograd.Function):
+    """Stem conv (5^3, tiny Cin): SIMT forward, weight gradient per tap; the input carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, nbr):
+        cout, cin = weight.shape[0], weight.shape[-1]
+        k3 = weight.numel() // (cout * cin)
+        wt = weight.detach().reshape(cout, k3, cin).permute(1, 2, 0).contiguous().float()  # [k3, cin, cout]
+        y = ops.subm_conv_simt(x, nbr, wt, None, out_dtype=torch.float32)
+        ctx.save_for_backward(x, weight, nbr)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, nbr = ctx.saved_tensors
+        cout, cin = weight.shape[0], weight.shape[-1]
+        k3 = weight.numel() // (cout * cin)
+        dy = dy.float()
+        dw = torch.zeros((k3, cin, cout), dtype=torch.float32, device=x.device)
+        for t in range(k3):
+            q = nbr[t]
+            p = (q >= 0).nonzero(as_tuple=True)[0]
+            if p.numel():
+                dw[t] = x[q[p].long()].float().t() @ dy[p]
+        return None, dw.permute(2, 0, 1).reshape(weight.shape).to(weight.dtype), None
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _patch_indices(point, table, K, order_row):
+    """[P, K] row indices of the queries / keys of every live patch (n = padding), cached on the Point."""
+    cache = point.setdefault("_patch_index", {})
+    key = (K, order_row.data_ptr())
+    if key not in cache:
+        n = order_row.shape[0]
+        t = table.cpu().long()
+        t = t[t[:, 1] > t[:, 0]]
+        ar = torch.arange(K)
+        q_pos = t[:, 0:1] + ar[None]
+        kv_pos = t[:, 2:3] + ar[None]
+        q_ok, kv_ok = q_pos < t[:, 1:2], kv_pos < t[:, 3:4]
+        dev = order_row.device
+        q_idx = torch.where(q_ok.to(dev), order_row[q_pos.clamp(max=n - 1).to(dev)], torch.full((1,), n, device=dev))
+        kv_idx = torch.where(kv_ok.to(dev), order_row[kv_pos.clamp(max=n - 1).to(dev)], torch.full((1,), n, device=dev))
+        cache[key] = (q_idx, kv_idx, kv_ok.to(dev))
+    return cache[key]
+
+
+def _attention_torch(qkv, q_idx, kv_idx, kv_ok, H, scale):
+    """The same patch attention with torch operators (differentiable): used for the backward recomputation."""
+    n, c3 = qkv.shape
+    C = c3 // 3
+    d = C // H
+    pad = torch.cat([qkv, qkv.new_zeros(1, c3)], 0)
+    P, K = q_idx.shape
+    q = pad[q_idx][..., :C].reshape(P, K, H, d).transpose(1, 2)
+    kv = pad[kv_idx]
+    k = kv[..., C:2 * C].reshape(P, K, H, d).transpose(1, 2)
+    v = kv[..., 2 * C:].reshape(P, K, H, d).transpose(1, 2)
+    o = F.scaled_dot_product_attention(q, k, v, attn_mask=kv_ok[:, None, None, :], scale=scale)
+    o = o.transpose(1, 2).reshape(P * K, C)
+    out = qkv.new_zeros(n + 1, C).index_copy(0, q_idx.reshape(-1), o)
+    return out[:n]
+
+
+class PatchAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, order_row, table, K, H, scale, idx):
+        out = ops.patch_attention(qkv, order_row, table, K, H, scale)
+        ctx.save_for_backward(qkv)
+        ctx.idx, ctx.H, ctx.scale = idx, H, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        q_idx, kv_idx, kv_ok = ctx.idx
+        with torch.enable_grad():
+            x = qkv.detach().requires_grad_(True)
+            o = _attention_torch(x, q_idx, kv_idx, kv_ok, ctx.H, ctx.scale)
+            (dqkv,) = torch.autograd.grad(o, x, dout.to(o.dtype))
+        return dqkv, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ pooling
+class SegmentMeanFn(torch.autograd.Function):
+    """out[m] = mean_{j in [seg_start[m], seg_start[m+1])} src[order0[j]]   (replaces torch_scatter.segment_csr)."""
+
+    @staticmethod
+    def forward(ctx, src, order0, seg_start):
+        out = ops.segment_reduce(src, order0, seg_start, "mean", out_dtype=torch.float32)
+        ctx.save_for_backward(order0, seg_start)
+        ctx.shape, ctx.dtype = src.shape, src.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        order0, seg_start = ctx.saved_tensors
+        cnt = seg_start[1:] - seg_start[:-1]
+        seg = torch.repeat_interleave(torch.arange(cnt.numel(), device=dout.device), cnt, output_size=ctx.shape[0])
+        d = (dout / cnt.clamp(min=1)[:, None].to(dout.dtype))[seg]
+        dsrc = torch.empty(ctx.shape, dtype=ctx.dtype, device=dout.device)
+        dsrc[order0] = d.to(ctx.dtype)
+        return dsrc, None, None
+
+
+# ------------------------------------------------------------------------------------------------ model walk
+def _lin(m: nn.Linear, x):
+    return F.linear(x.to(BF16), m.weight.to(BF16), m.bias.to(BF16) if m.bias is not None else None)
+
+
+def _ln(m: nn.LayerNorm, x):
+    return F.layer_norm(x.float(), m.normalized_shape, m.weight, m.bias, m.eps)
+
+
+def _bn(m, x):
+    """BatchNorm1d in the module's own mode (batch statistics + running-stat update when training)."""
+    return m(x.float()) if m is not None else x
+
+
+def _drop_path(seq, x):
+    for m in seq.modules():
+        if type(m).__name__ == "DropPath":
+            return m(x)
+    return x
+
+
+def _pairs(point):
+    ent = kernel_map_for(point, 3, want_pairs=True)
+    return ent["pairs"]
+
+
+def block_train(blk, point, x, conv_src=None):
+    """Block.forward (ref :318-338) under autograd.  x: fp32 residual stream [N, C]."""
+    conv, cpe_lin, cpe_ln = blk.cpe[0], blk.cpe[1], blk.cpe[2]
+    src = x if conv_src is None else conv_src
+    y = SubMConvFn.apply(src.to(BF16), conv.weight, conv.bias, _pairs(point), x.shape[0])
+    x = x + _ln(cpe_ln, _lin(cpe_lin, y))
+    att = blk.attn
+    h = _ln(blk.norm1[0], x)
+    qkv = _lin(att.qkv, h)
+    table = att.patch_table(point)
+    order_row = point.serialized_order[att.order_index].contiguous()
+    idx = _patch_indices(point, table, att.patch_size, order_row)
+    a = PatchAttentionFn.apply(qkv, order_row, table, att.patch_size, att.num_heads, att.scale, idx)
+    x = x + _drop_path(blk.drop_path, _lin(att.proj, a).float())
+    h = _ln(blk.norm2[0], x)
+    mlp = blk.mlp[0]
+    m = _lin(mlp.fc2, F.gelu(_lin(mlp.fc1, h)))
+    x = x + _drop_path(blk.drop_path, m.float())
+    return x
+
+
+def pooling_train(down, point, x):
+    """SerializedPooling.forward (ref :371-444) under autograd; indices from the plan built by `prepare`."""
+    plan = point["_pool_plan"]
+    perm, ix = plan["perm"], plan["ix"]
+    if down.reduce != "mean":
+        raise NotImplementedError("training path: SerializedPooling(reduce='mean') only (the lang configs)")
+    order0 = point.serialized_order[0].contiguous()
+    feat = SegmentMeanFn.apply(_lin(down.proj, x), order0, ix["seg_start"])
+    coord = ops.segment_reduce(point.coord.float(), order0, ix["seg_start"], "mean")
+    names = point.serialized_order_names
+    n_batch = point.offset.numel()
+    offset = torch.searchsorted(ix["batch"], torch.arange(n_batch, device=feat.device), right=True)
+    child = Point(Dict(feat=feat, coord=coord, grid_coord=ix["grid_coord"], serialized_code=ix["code"],
+                       serialized_order=ix["order"], serialized_inverse=ix["inverse"],
+                       serialized_depth=point.serialized_depth - plan["pooling_depth"], batch=ix["batch"], offset=offset,
+                       serialized_order_names=tuple(names[i] for i in perm)))
+    child["_kmap_cache"] = plan["kmap_cache"]
+    if plan.get("child") is not None:
+        child["_pool_plan"] = plan["child"]
+    if getattr(down, "norm", None) is not None:
+        feat = _bn(down.norm[0], feat)
+    if getattr(down, "act", None) is not None:
+        feat = F.gelu(feat)
+    return child, feat, ix["cluster"]
+
+
+def unpool_train(up, x_child, cluster, x_parent):
+    """SerializedUnpooling.forward (ref :471-482) under autograd -> (parent feat, skip branch alone)."""
+    lin_p, bn_p, act_p, _ = up._branch(up.proj)
+    lin_s, bn_s, act_s, _ = up._branch(up.proj_skip)
+    a = _bn(bn_p, _lin(lin_p, x_child).float())
+    s = _bn(bn_s, _lin(lin_s, x_parent).float())
+    if act_p is not None:
+        a = F.gelu(a)
+    if act_s is not None:
+        s = F.gelu(s)
+    return s + a[cluster], s
+
+
+def forward_train(model, data_dict):
+    """PointTransformerV3.forward (ref :699-714) under autograd -> fp32 features [N, C_dec0]."""
+    point = model.prepare(data_dict)
+    stem = model.embedding.stem._modules
+    ent = kernel_map_for(point, stem["conv"].kernel_size, want_pairs=False)
+    x = StemConvFn.apply(point.feat.float().contiguous(), stem["conv"].weight, ent["nbr"])
+    if "norm" in stem:
+        x = _bn(stem["norm"], x)
+    if "act" in stem:
+        x = F.gelu(x)
+    skips = []
+    for stage in model.enc.children():
+        down = getattr(stage, "down", None)
+        if down is not None:
+            skips.append((point, x))
+            point, x, cluster = pooling_train(down, point, x)
+            skips[-1] = skips[-1] + (cluster,)
+        for name, blk in stage.named_children():
+            if name != "down":
+                x = block_train(blk, point, x)
+    if model.cls_mode:
+        return x
+    for stage in model.dec.children():
+        parent, x_parent, cluster = skips.pop()
+        x, skip_only = unpool_train(stage.up, x, cluster, x_parent)
+        point = parent
+        first = True
+        for name, blk in stage.named_children():
+            if name != "up":
+                # ref quirk: after unpooling, sparse_conv_feat still holds the skip projection alone (see ptv3.py)
+                x = block_train(blk, point, x, conv_src=skip_only if first else None)
+                first = False
+    return x
+
+
+# ------------------------------------------------------------------------------------------------ losses (autograd)
+def cosine_loss(pred, target, mask, loss_weight=1.0):
+    """losses/misc.py:254-270"""
+    m = mask.bool()
+    if not m.any():
+        return pred.sum() * 0.0
+    return loss_weight * (1.0 - F.cosine_similarity(pred[m].float(), target[m].float(), dim=1, eps=1e-8)).mean()
+
+
+def l2_loss(pred, target, mask, loss_weight=1.0):
+    """losses/misc.py:280-295"""
+    m = mask.bool()
+    if not m.any():
+        return pred.sum() * 0.0
+    return loss_weight * ((pred[m].float() - target[m].float()) ** 2).sum(1).mean()
+
+
+def class_half_sums(pred, valid, segment, half, n_classes):
+    """Per (class, half) feature sums with torch index_add (differentiable twin of ops.class_half_sums)."""
+    key = segment.long().clamp(min=0) * 2 + half.long()
+    w = valid.to(pred.dtype)[:, None]
+    sums = pred.new_zeros(2 * n_classes, pred.shape[1]).index_add(0, key, pred * w)
+    counts = torch.zeros(2 * n_classes, dtype=torch.long, device=pred.device).index_add(0, key, valid.long())
+    return sums, counts
