@@ -72,11 +72,14 @@ class SubMConvFn(torch.autograd.Function):
             wt = weight.detach().reshape(cout, k3, cin).permute(1, 2, 0).flip(0).contiguous().to(BF16)  # [k3, cin, cout]
             dx = ops.subm_conv_gemm(dy, pairs, wt, None, n, out_dtype=BF16)
         if ctx.needs_input_grad[1]:
-            pin, pout = pairs["pair_in"].long(), _pair_out(pairs)
-            dw = torch.zeros((k3, cout, cin), dtype=torch.float32, device=x.device)
+            # dW_t = dY[pair_out(t)]^T X[pair_in(t)]: both operands gathered once for all taps, one GEMM per tap segment
+            xg = ops.gather_rows(x, pairs["pair_in_i64"] if "pair_in_i64" in pairs else pairs.setdefault(
+                "pair_in_i64", pairs["pair_in"].long()))
+            dyg = ops.gather_rows(dy, _pair_out(pairs))
+            dw = torch.zeros((k3, cout, cin), dtype=BF16, device=x.device)
             for t, (b0, c) in enumerate(zip(pairs["tap_base"], pairs["tap_count"])):
                 if c > 0:
-                    dw[t] = torch.mm(dy[pout[b0:b0 + c]].t(), x[pin[b0:b0 + c]]).float()
+                    torch.mm(dyg[b0:b0 + c].t(), xg[b0:b0 + c], out=dw[t])
             dw = dw.permute(1, 0, 2).reshape(weight.shape).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(0)
@@ -101,67 +104,82 @@ class StemConvFn(torch.autograd.Function):
         cout, cin = weight.shape[0], weight.shape[-1]
         k3 = weight.numel() // (cout * cin)
         dy = dy.float()
-        dw = torch.zeros((k3, cin, cout), dtype=torch.float32, device=x.device)
-        for t in range(k3):
-            q = nbr[t]
-            p = (q >= 0).nonzero(as_tuple=True)[0]
-            if p.numel():
-                dw[t] = x[q[p].long()].float().t() @ dy[p]
+        n = x.shape[0]
+        xp = torch.cat([x.float(), x.new_zeros(1, cin, dtype=torch.float32)], 0)
+        idx = torch.where(nbr >= 0, nbr, torch.full_like(nbr, n)).long()  # [k3, n]; missing neighbour -> the zero row
+        dw = torch.matmul(xp[idx].transpose(1, 2), dy)                      # [k3, cin, n] @ [n, cout]
         return None, dw.permute(2, 0, 1).reshape(weight.shape).to(weight.dtype), None
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def _patch_indices(point, table, K, order_row):
-    """[P, K] row indices of the queries / keys of every live patch (n = padding), cached on the Point."""
-    cache = point.setdefault("_patch_index", {})
-    key = (K, order_row.data_ptr())
-    if key not in cache:
-        n = order_row.shape[0]
-        t = table.cpu().long()
-        t = t[t[:, 1] > t[:, 0]]
-        ar = torch.arange(K)
-        q_pos = t[:, 0:1] + ar[None]
-        kv_pos = t[:, 2:3] + ar[None]
-        q_ok, kv_ok = q_pos < t[:, 1:2], kv_pos < t[:, 3:4]
-        dev = order_row.device
-        q_idx = torch.where(q_ok.to(dev), order_row[q_pos.clamp(max=n - 1).to(dev)], torch.full((1,), n, device=dev))
-        kv_idx = torch.where(kv_ok.to(dev), order_row[kv_pos.clamp(max=n - 1).to(dev)], torch.full((1,), n, device=dev))
-        cache[key] = (q_idx, kv_idx, kv_ok.to(dev))
-    return cache[key]
+def _patch_plan(point, K):
+    """Patch layout of every batch item in SORTED positions (ref :114-170), from the offsets on the host:
+    [(start, n_full_patches, tail_rows, end)], cached on the Point."""
+    cache = point.setdefault("_patch_plan", {})
+    if K not in cache:
+        off = [0] + [int(v) for v in point.offset.cpu().tolist()]
+        plan = []
+        for s0, e0 in zip(off[:-1], off[1:]):
+            nb = e0 - s0
+            if nb <= 0:
+                continue
+            if nb <= K:
+                plan.append((s0, 0, nb, e0))       # one short sequence: queries = keys = the whole item
+            else:
+                plan.append((s0, nb // K, nb - (nb // K) * K, e0))
+        cache[K] = plan
+    return cache[K]
 
 
-def _attention_torch(qkv, q_idx, kv_idx, kv_ok, H, scale):
-    """The same patch attention with torch operators (differentiable): used for the backward recomputation."""
-    n, c3 = qkv.shape
-    C = c3 // 3
+def _sdpa(q, k, v, H, scale):
+    """q [P, Lq, C], k / v [P, Lk, C] -> [P, Lq, C] with H heads (torch's fused attention, differentiable)."""
+    P, Lq, C = q.shape
     d = C // H
-    pad = torch.cat([qkv, qkv.new_zeros(1, c3)], 0)
-    P, K = q_idx.shape
-    q = pad[q_idx][..., :C].reshape(P, K, H, d).transpose(1, 2)
-    kv = pad[kv_idx]
-    k = kv[..., C:2 * C].reshape(P, K, H, d).transpose(1, 2)
-    v = kv[..., 2 * C:].reshape(P, K, H, d).transpose(1, 2)
-    o = F.scaled_dot_product_attention(q, k, v, attn_mask=kv_ok[:, None, None, :], scale=scale)
-    o = o.transpose(1, 2).reshape(P * K, C)
-    out = qkv.new_zeros(n + 1, C).index_copy(0, q_idx.reshape(-1), o)
-    return out[:n]
+    sp = lambda t: t.reshape(P, t.shape[1], H, d).transpose(1, 2)
+    o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v), scale=scale)
+    return o.transpose(1, 2).reshape(P, Lq, C)
+
+
+def _attention_torch(qkv, order_row, plan, K, H, scale):
+    """The same patch attention with torch operators (differentiable): used for the backward recomputation.  Works in
+    sorted space, where every patch is a contiguous row range: full patches are one batched call on a view, the
+    last patch of an item attends to the window of its last K rows and keeps its own tail rows."""
+    C = qkv.shape[1] // 3
+    xs = qkv.index_select(0, order_row)
+    outs = []
+    mains = [xs[s0:s0 + nf * K].view(nf, K, 3 * C) for s0, nf, _, _ in plan if nf > 0]
+    om = None
+    if mains:
+        m = torch.cat(mains, 0) if len(mains) > 1 else mains[0]
+        om = _sdpa(m[..., :C], m[..., C:2 * C], m[..., 2 * C:], H, scale).reshape(-1, C)
+    pos = 0
+    for s0, nf, r, e0 in plan:
+        if nf > 0:
+            outs.append(om[pos:pos + nf * K])
+            pos += nf * K
+        if r > 0:
+            kv = xs[max(e0 - K, s0):e0].unsqueeze(0)
+            q = xs[e0 - r:e0].unsqueeze(0)
+            outs.append(_sdpa(q[..., :C], kv[..., C:2 * C], kv[..., 2 * C:], H, scale)[0])
+    out_s = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+    out = torch.empty_like(out_s)
+    return out.index_copy(0, order_row, out_s)
 
 
 class PatchAttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, order_row, table, K, H, scale, idx):
+    def forward(ctx, qkv, order_row, table, K, H, scale, plan):
         out = ops.patch_attention(qkv, order_row, table, K, H, scale)
-        ctx.save_for_backward(qkv)
-        ctx.idx, ctx.H, ctx.scale = idx, H, scale
+        ctx.save_for_backward(qkv, order_row)
+        ctx.plan, ctx.K, ctx.H, ctx.scale = plan, K, H, scale
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (qkv,) = ctx.saved_tensors
-        q_idx, kv_idx, kv_ok = ctx.idx
+        qkv, order_row = ctx.saved_tensors
         with torch.enable_grad():
             x = qkv.detach().requires_grad_(True)
-            o = _attention_torch(x, q_idx, kv_idx, kv_ok, ctx.H, ctx.scale)
+            o = _attention_torch(x, order_row, ctx.plan, ctx.K, ctx.H, ctx.scale)
             (dqkv,) = torch.autograd.grad(o, x, dout.to(o.dtype))
         return dqkv, None, None, None, None, None, None
 
@@ -225,8 +243,8 @@ def block_train(blk, point, x, conv_src=None):
     qkv = _lin(att.qkv, h)
     table = att.patch_table(point)
     order_row = point.serialized_order[att.order_index].contiguous()
-    idx = _patch_indices(point, table, att.patch_size, order_row)
-    a = PatchAttentionFn.apply(qkv, order_row, table, att.patch_size, att.num_heads, att.scale, idx)
+    a = PatchAttentionFn.apply(qkv, order_row, table, att.patch_size, att.num_heads, att.scale,
+                               _patch_plan(point, att.patch_size))
     x = x + _drop_path(blk.drop_path, _lin(att.proj, a).float())
     h = _ln(blk.norm2[0], x)
     mlp = blk.mlp[0]
