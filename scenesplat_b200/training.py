@@ -131,57 +131,65 @@ def _patch_plan(point, K):
     return cache[K]
 
 
-def _sdpa(q, k, v, H, scale):
-    """q [P, Lq, C], k / v [P, Lk, C] -> [P, Lq, C] with H heads (torch's fused attention, differentiable)."""
-    P, Lq, C = q.shape
-    d = C // H
-    sp = lambda t: t.reshape(P, t.shape[1], H, d).transpose(1, 2)
-    o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v), scale=scale)
-    return o.transpose(1, 2).reshape(P, Lq, C)
+def _heads(t, H):
+    P, Lq, C = t.shape
+    return t.reshape(P, Lq, H, C // H).transpose(1, 2)
 
 
-def _attention_torch(qkv, order_row, plan, K, H, scale):
-    """The same patch attention with torch operators (differentiable): used for the backward recomputation.  Works in
-    sorted space, where every patch is a contiguous row range: full patches are one batched call on a view, the
-    last patch of an item attends to the window of its last K rows and keeps its own tail rows."""
+def _attention_backward(qkv, order_row, inverse_row, plan, K, H, scale, dout):
+    """d(qkv) of the patch attention, by recomputation with torch's fused attention (library; forward is the
+    package's tcgen05 kernel).  Everything happens in SORTED space, where a patch is a contiguous row range: the
+    rows are permuted in and out with the package's gather kernel (order / inverse are permutations, so both
+    directions are gathers), full patches are one batched call on a view, the last patch of an item attends to
+    the window of its last K rows and keeps its own tail rows."""
     C = qkv.shape[1] // 3
-    xs = qkv.index_select(0, order_row)
-    outs = []
-    mains = [xs[s0:s0 + nf * K].view(nf, K, 3 * C) for s0, nf, _, _ in plan if nf > 0]
-    om = None
+    xs = ops.gather_rows(qkv, order_row)        # [n, 3C] sorted
+    dos = ops.gather_rows(dout.contiguous(), order_row)
+    dxs = torch.zeros_like(xs)
+
+    def run(q, k, v, do):
+        q, k, v = (t.detach().requires_grad_(True) for t in (q, k, v))
+        with torch.enable_grad():
+            o = F.scaled_dot_product_attention(_heads(q, H), _heads(k, H), _heads(v, H), scale=scale)
+        return torch.autograd.grad(o, (q, k, v), _heads(do, H))
+
+    mains = [(s0, nf) for s0, nf, _, _ in plan if nf > 0]
     if mains:
-        m = torch.cat(mains, 0) if len(mains) > 1 else mains[0]
-        om = _sdpa(m[..., :C], m[..., C:2 * C], m[..., 2 * C:], H, scale).reshape(-1, C)
-    pos = 0
+        xm = [xs[s0:s0 + nf * K].view(nf, K, 3 * C) for s0, nf in mains]
+        dm = [dos[s0:s0 + nf * K].view(nf, K, C) for s0, nf in mains]
+        xm = torch.cat(xm, 0) if len(xm) > 1 else xm[0]
+        dm = torch.cat(dm, 0) if len(dm) > 1 else dm[0]
+        dq, dk, dv = run(xm[..., :C], xm[..., C:2 * C], xm[..., 2 * C:], dm)
+        g = torch.cat([dq, dk, dv], -1)
+        pos = 0
+        for s0, nf in mains:
+            dxs[s0:s0 + nf * K] = g[pos:pos + nf].reshape(nf * K, 3 * C)
+            pos += nf
     for s0, nf, r, e0 in plan:
-        if nf > 0:
-            outs.append(om[pos:pos + nf * K])
-            pos += nf * K
         if r > 0:
-            kv = xs[max(e0 - K, s0):e0].unsqueeze(0)
+            w0 = max(e0 - K, s0)
+            kv = xs[w0:e0].unsqueeze(0)
             q = xs[e0 - r:e0].unsqueeze(0)
-            outs.append(_sdpa(q[..., :C], kv[..., C:2 * C], kv[..., 2 * C:], H, scale)[0])
-    out_s = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
-    out = torch.empty_like(out_s)
-    return out.index_copy(0, order_row, out_s)
+            dq, dk, dv = run(q[..., :C], kv[..., C:2 * C], kv[..., 2 * C:], dos[e0 - r:e0].unsqueeze(0))
+            dxs[e0 - r:e0, :C] += dq[0]
+            dxs[w0:e0, C:2 * C] += dk[0]
+            dxs[w0:e0, 2 * C:] += dv[0]
+    return ops.gather_rows(dxs, inverse_row)
 
 
 class PatchAttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, order_row, table, K, H, scale, plan):
+    def forward(ctx, qkv, order_row, inverse_row, table, K, H, scale, plan):
         out = ops.patch_attention(qkv, order_row, table, K, H, scale)
-        ctx.save_for_backward(qkv, order_row)
+        ctx.save_for_backward(qkv, order_row, inverse_row)
         ctx.plan, ctx.K, ctx.H, ctx.scale = plan, K, H, scale
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, order_row = ctx.saved_tensors
-        with torch.enable_grad():
-            x = qkv.detach().requires_grad_(True)
-            o = _attention_torch(x, order_row, ctx.plan, ctx.K, ctx.H, ctx.scale)
-            (dqkv,) = torch.autograd.grad(o, x, dout.to(o.dtype))
-        return dqkv, None, None, None, None, None, None
+        qkv, order_row, inverse_row = ctx.saved_tensors
+        dqkv = _attention_backward(qkv, order_row, inverse_row, ctx.plan, ctx.K, ctx.H, ctx.scale, dout.to(qkv.dtype))
+        return dqkv, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------ pooling
@@ -243,7 +251,8 @@ def block_train(blk, point, x, conv_src=None):
     qkv = _lin(att.qkv, h)
     table = att.patch_table(point)
     order_row = point.serialized_order[att.order_index].contiguous()
-    a = PatchAttentionFn.apply(qkv, order_row, table, att.patch_size, att.num_heads, att.scale,
+    inverse_row = point.serialized_inverse[att.order_index].contiguous()
+    a = PatchAttentionFn.apply(qkv, order_row, inverse_row, table, att.patch_size, att.num_heads, att.scale,
                                _patch_plan(point, att.patch_size))
     x = x + _drop_path(blk.drop_path, _lin(att.proj, a).float())
     h = _ln(blk.norm2[0], x)
