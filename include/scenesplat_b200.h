@@ -189,6 +189,13 @@ int ss_lang_head_tc(const void* feat_bf16, const void* text_bf16, int64_t n, int
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training path adjoints.  LayerNorm backward (torch nn.LayerNorm in the reference's Block,
+ * point_transformer_v3m1_base.py:277-338): dx = d/dx of LN(x; gamma, beta) contracted with dy, in x's dtype;
+ * dgamma / dbeta (fp32, [channels]) are ACCUMULATED: zero them first.  channels % 8 == 0, <= 1024. */
+int ss_layernorm_backward(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, const float* gamma, float eps,
+                          int64_t n, int channels, void* dx, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SphereCrop (pointcept/datasets/transform.py:1419-1535, modes "random" / "center"): order[j] = index of the j-th
  * nearest point to `center3` (HOST pointer, 3 floats), distances in numpy's fp32 arithmetic, ties by ascending
  * index; dist_bits_sorted[j] = bit pattern of that squared distance (low 32 bits). */

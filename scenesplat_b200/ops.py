@@ -292,6 +292,18 @@ def add_layernorm(res, delta, ln0=None, ln1=None, eps=1e-5, want_res=True, norm_
     return res_out, norm_out
 
 
+def layernorm_backward(x, dy, gamma, eps=1e-5):
+    """-> (dx in x's dtype, dgamma fp32 [C], dbeta fp32 [C]) of y = LayerNorm(x; gamma, beta) contracted with dy."""
+    x, dy = x.contiguous(), dy.contiguous()
+    n, c = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.zeros(c, dtype=torch.float32, device=x.device)
+    db = torch.zeros(c, dtype=torch.float32, device=x.device)
+    L.call("ss_layernorm_backward", L.ptr(x), _isbf(x), L.ptr(dy), _isbf(dy), L.ptr(gamma), float(eps), n, c, L.ptr(dx),
+           L.ptr(dg), L.ptr(db), L.stream())
+    return dx, dg, db
+
+
 def affine_act(x, scale=None, shift=None, act=0, out_dtype=None):
     x = x.contiguous()
     n, c = x.shape

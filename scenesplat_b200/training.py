@@ -219,8 +219,36 @@ def _lin(m: nn.Linear, x):
     return F.linear(x.to(BF16), m.weight.to(BF16), m.bias.to(BF16) if m.bias is not None else None)
 
 
-def _ln(m: nn.LayerNorm, x):
-    return F.layer_norm(x.float(), m.normalized_shape, m.weight, m.bias, m.eps)
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the channel dim: forward = the fused row kernel of the inference path (fp32 or bf16 in,
+    fp32 or bf16 out, no separate cast passes), backward = csrc/backward.cu (one pass over x and dy)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        x = x.contiguous()
+        if x.dtype == torch.float32:
+            _, y = ops.add_layernorm(x, None, None, (w, b), eps, want_res=False, norm_dtype=out_dtype)
+        elif out_dtype == torch.float32:
+            y, _ = ops.add_layernorm(None, x, (w, b), None, eps, want_res=True)
+        else:
+            _, y = ops.add_layernorm(None, x, (w, b), None, eps, want_res=False, norm_dtype=out_dtype)
+        ctx.save_for_backward(x, w)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_backward(x, dy, w, ctx.eps)
+        return dx, dg, db, None, None
+
+
+def _ln(m: nn.LayerNorm, x, out_dtype=torch.float32):
+    c = x.shape[1]
+    if c % 8 == 0 and c <= 1024 and x.dtype in (torch.float32, BF16):
+        return LayerNormFn.apply(x, m.weight, m.bias, m.eps, out_dtype)
+    return F.layer_norm(x.float(), m.normalized_shape, m.weight, m.bias, m.eps).to(out_dtype)
 
 
 def _bn(m, x):
@@ -247,7 +275,7 @@ def block_train(blk, point, x, conv_src=None):
     y = SubMConvFn.apply(src.to(BF16), conv.weight, conv.bias, _pairs(point), x.shape[0])
     x = x + _ln(cpe_ln, _lin(cpe_lin, y))
     att = blk.attn
-    h = _ln(blk.norm1[0], x)
+    h = _ln(blk.norm1[0], x, BF16)
     qkv = _lin(att.qkv, h)
     table = att.patch_table(point)
     order_row = point.serialized_order[att.order_index].contiguous()
@@ -255,7 +283,7 @@ def block_train(blk, point, x, conv_src=None):
     a = PatchAttentionFn.apply(qkv, order_row, inverse_row, table, att.patch_size, att.num_heads, att.scale,
                                _patch_plan(point, att.patch_size))
     x = x + _drop_path(blk.drop_path, _lin(att.proj, a).float())
-    h = _ln(blk.norm2[0], x)
+    h = _ln(blk.norm2[0], x, BF16)
     mlp = blk.mlp[0]
     m = _lin(mlp.fc2, F.gelu(_lin(mlp.fc1, h)))
     x = x + _drop_path(blk.drop_path, m.float())

@@ -113,3 +113,27 @@ def test_lang_pretrainer_training_step():
     opt.step()
     moved = sum(int(not torch.equal(before[k], v.detach())) for k, v in model.named_parameters())
     assert moved == len(before)
+
+
+@pytest.mark.parametrize("c,xdt,dydt", [(32, torch.float32, torch.float32), (768, torch.float32, torch.bfloat16),
+                                        (512, torch.bfloat16, torch.float32), (1024, torch.bfloat16, torch.bfloat16),
+                                        (96, torch.float32, torch.float32)])
+def test_layernorm_backward_kernel(c, xdt, dydt):
+    """csrc/backward.cu vs torch autograd of F.layer_norm in fp32 on the same (possibly bf16-rounded) inputs:
+    fp32 arithmetic on both sides, 2e-4 relative (1e-2 on dx when dx is stored as bf16)."""
+    from scenesplat_b200 import ops
+    torch.manual_seed(c)
+    n = 3001
+    x = (torch.randn(n, c) * 2 + 0.5).to(xdt)
+    dy = torch.randn(n, c).to(dydt)
+    g, b = torch.rand(c) + 0.5, torch.randn(c)
+    xr = x.float().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (c,), gr, br, 1e-5).backward(dy.float())
+    dx, dg, db = ops.layernorm_backward(x.cuda(), dy.cuda(), g.cuda(), 1e-5)
+    assert dx.dtype == xdt
+    tol = 1e-2 if xdt == torch.bfloat16 else 2e-4
+    assert ((dx.float().cpu() - xr.grad).norm() / xr.grad.norm()).item() < tol
+    assert ((dg.cpu() - gr.grad).norm() / gr.grad.norm()).item() < 2e-4
+    assert ((db.cpu() - br.grad).norm() / br.grad.norm()).item() < 2e-4
