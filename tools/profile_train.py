@@ -10,4 +10,4 @@ step = ns["step"]
 step(); torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+print(prof.key_averages().table(sort_by=os.environ.get("PROF_SORT", "cuda_time_total"), row_limit=40, max_name_column_width=70))
