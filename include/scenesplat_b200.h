@@ -192,6 +192,12 @@ int ss_lang_head_tc(const void* feat_bf16, const void* text_bf16, int64_t n, int
  * Training path adjoints.  LayerNorm backward (torch nn.LayerNorm in the reference's Block,
  * point_transformer_v3m1_base.py:277-338): dx = d/dx of LN(x; gamma, beta) contracted with dy, in x's dtype;
  * dgamma / dbeta (fp32, [channels]) are ACCUMULATED: zero them first.  channels % 8 == 0, <= 1024. */
+/* Weight gradient of the 3^3 submanifold conv on the tensor cores: dw[t][co][ci] += sum over the pairs r of the K chunks
+ * of tap t of dy[pair_out[r]][co] * x[pair_in[r]][ci].  chunks: [n_chunks] int32x4 (tap, k_begin, k_end, 0) over the pair
+ * lists of ss_kmap_pairs (exact ranges: padding rows excluded); dw fp32 [k3, cout, cin], ACCUMULATED (zero it first);
+ * cin, cout multiples of 32. */
+int ss_subm_conv_wgrad(const void* x_bf16, const void* dy_bf16, const int32_t* pair_in, const int64_t* pair_out,
+                       const int32_t* chunks, int n_chunks, int k3, int cin, int cout, float* dw, void* stream);
 int ss_layernorm_backward(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, const float* gamma, float eps,
                           int64_t n, int channels, void* dx, float* dgamma, float* dbeta, void* stream);
 

@@ -292,6 +292,24 @@ def add_layernorm(res, delta, ln0=None, ln1=None, eps=1e-5, want_res=True, norm_
     return res_out, norm_out
 
 
+def subm_conv_wgrad(x_bf16, dy_bf16, pairs, pair_out, k3, rows_per_chunk=8192):
+    """-> dw fp32 [k3, cout, cin] = per-tap dY[pair_out]^T X[pair_in] on the tensor cores (split-K over pair chunks)."""
+    cin, cout = x_bf16.shape[1], dy_bf16.shape[1]
+    key = ("wgrad_chunks", rows_per_chunk)
+    if key not in pairs:
+        rows = []
+        for t, (b0, c) in enumerate(zip(pairs["tap_base"], pairs["tap_count"])):
+            for k in range(b0, b0 + c, rows_per_chunk):
+                rows.append((t, k, min(k + rows_per_chunk, b0 + c), 0))
+        pairs[key] = torch.tensor(rows or [(0, 0, 0, 0)], dtype=torch.int32, device=x_bf16.device), len(rows)
+    chunks, n_chunks = pairs[key]
+    dw = torch.zeros((k3, cout, cin), dtype=torch.float32, device=x_bf16.device)
+    L.call("ss_subm_conv_wgrad", L.ptr(x_bf16.contiguous()), L.ptr(dy_bf16.contiguous()), L.ptr(pairs["pair_in"]),
+           L.ptr(pair_out), L.ptr(chunks), n_chunks, k3, cin, cout, L.ptr(dw), L.stream(),
+           meta=dict(flops=2.0 * pairs["pairs"] * cin * cout))
+    return dw
+
+
 def layernorm_backward(x, dy, gamma, eps=1e-5):
     """-> (dx in x's dtype, dgamma fp32 [C], dbeta fp32 [C]) of y = LayerNorm(x; gamma, beta) contracted with dy."""
     x, dy = x.contiguous(), dy.contiguous()

@@ -9,8 +9,7 @@ that structure: Linear / LayerNorm / BatchNorm(train) / GELU / DropPath / residu
   SubMConvFn      forward: tcgen05 gather-GEMM + gather-sum (csrc/conv_gemm2.cu, conv_gemm.cu)
                   dgrad:   THE SAME kernels on the mirrored taps with transposed weights (the submanifold kernel map is
                            symmetric: nbr[t][p] = q  <=>  nbr[26-t][q] = p)
-                  wgrad:   per-tap GEMM dY[pair_out]^T X[pair_in] (gathers + cuBLASLt)         [library GEMM, round 2:
-                           gathered-A x gathered-B tcgen05 kernel]
+                  wgrad:   gathered-A x gathered-B tcgen05 GEMM per tap, split-K over pair chunks (csrc/conv_wgrad.cu)
   StemConvFn      forward: csrc/conv_simt.cu; wgrad per tap (the stem's input needs no gradient)
   PatchAttentionFn forward: tcgen05 patch attention (csrc/attention_tc.cu)
                   backward: recomputation with torch's fused SDPA on the gathered patches       [library, round 2:
@@ -72,14 +71,8 @@ class SubMConvFn(torch.autograd.Function):
             wt = weight.detach().reshape(cout, k3, cin).permute(1, 2, 0).flip(0).contiguous().to(BF16)  # [k3, cin, cout]
             dx = ops.subm_conv_gemm(dy, pairs, wt, None, n, out_dtype=BF16)
         if ctx.needs_input_grad[1]:
-            # dW_t = dY[pair_out(t)]^T X[pair_in(t)]: both operands gathered once for all taps, one GEMM per tap segment
-            xg = ops.gather_rows(x, pairs["pair_in_i64"] if "pair_in_i64" in pairs else pairs.setdefault(
-                "pair_in_i64", pairs["pair_in"].long()))
-            dyg = ops.gather_rows(dy, _pair_out(pairs))
-            dw = torch.zeros((k3, cout, cin), dtype=BF16, device=x.device)
-            for t, (b0, c) in enumerate(zip(pairs["tap_base"], pairs["tap_count"])):
-                if c > 0:
-                    torch.mm(dyg[b0:b0 + c].t(), xg[b0:b0 + c], out=dw[t])
+            # dW_t = dY[pair_out(t)]^T X[pair_in(t)]: gathered-operand GEMM on the tensor cores (csrc/conv_wgrad.cu)
+            dw = ops.subm_conv_wgrad(x, dy, pairs, _pair_out(pairs), k3)
             dw = dw.permute(1, 0, 2).reshape(weight.shape).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(0)

@@ -137,3 +137,38 @@ def test_layernorm_backward_kernel(c, xdt, dydt):
     assert ((dx.float().cpu() - xr.grad).norm() / xr.grad.norm()).item() < tol
     assert ((dg.cpu() - gr.grad).norm() / gr.grad.norm()).item() < 2e-4
     assert ((db.cpu() - br.grad).norm() / br.grad.norm()).item() < 2e-4
+
+
+@pytest.mark.parametrize("c", [32, 64, 256, 768])
+def test_conv_backward_kernels(c):
+    """SubMConvFn (own forward, own dgrad on the mirrored taps, own tensor-core wgrad) vs torch autograd through
+    the fp32 oracle conv on the same bf16-rounded operands: bf16 products, fp32 accumulation -> 1e-2 relative L2."""
+    from oracle import serialization as oser
+    from oracle import subm_conv as oconv
+    from scenesplat_b200 import ops, training
+    d = synthetic.chunk(6000 if c > 256 else 12000, L=3.0, H=2.0, seed=2)
+    res = ogs.grid_sample_train(d["coord"], 0.02)
+    g = res["grid_coord"]
+    n = g.shape[0]
+    offset = np.array([n // 3, n], dtype=np.int64)
+    batch = oser.offset2batch(offset)
+    code, order, inv, depth = oser.serialization(g, batch, 2, ("z",))
+    torch.manual_seed(1)
+    x = torch.randn(n, c).bfloat16()
+    w = (torch.randn(c, 3, 3, 3, c) * (1.0 / (c * 7) ** 0.5)).bfloat16().float()
+    b = torch.randn(c)
+    G = torch.randn(n, c).bfloat16()
+    # oracle
+    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    nbr_ref = oconv.kernel_map(g, batch, 3)
+    (oconv.subm_conv(xr, nbr_ref, wr, br) * G.float()).sum().backward()
+    # product
+    dev = lambda a: torch.as_tensor(a).cuda()
+    nbr, cnt = ops.kmap_build(dev(g), dev(batch), dev(code[0]), dev(order[0]), depth, 0, 3)
+    pairs = ops.kmap_pairs(nbr, dev(order[0]), 3, cnt.cpu().numpy())
+    xg, wg, bg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = training.SubMConvFn.apply(xg, wg, bg, pairs, n)
+    (y.float() * G.cuda().float()).sum().backward()
+    for name, got, want in (("dx", xg.grad, xr.grad), ("dw", wg.grad, wr.grad), ("db", bg.grad, br.grad)):
+        rel = ((got.float().cpu() - want).norm() / want.norm()).item()
+        assert rel < 1e-2, (name, rel)
