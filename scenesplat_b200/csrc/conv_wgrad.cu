@@ -12,8 +12,8 @@
 // the partial tile is added to the fp32 dW with vector reductions (red.global.add.v4.f32; the summation order
 // over the chunks is not fixed, as in every split-K weight gradient).
 //
-// 18 warps: 0-7 epilogue (TMEM -> red.global), 8-15 gather producers (cp.async, 16 per thread and stage, published
-// with cp.async.mbarrier.arrive.noinc), 16 idle, 17 MMA issuer.
+// 18 warps: 0-7 epilogue (TMEM -> red.global), 8-11 / 12-15 gather producers of dY / X (cp.async, 16 per thread and
+// stage, whole 32-byte sectors per instruction, published with cp.async.mbarrier.arrive.noinc), 16 idle, 17 MMA issuer.
 #include "tc_common.cuh"
 #include "../../include/scenesplat_b200.h"
 
@@ -70,9 +70,14 @@ conv_wgrad_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __re
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8 && warp < 16) {
-    // ------------------------------------------------------------------ gather producers: thread = (row j, quarter q)
-    const int tid = threadIdx.x - 256;
-    const int j = tid >> 2, q = tid & 3;
+    // ------------------------------------------------------------------ gather producers
+    // warps 8-11 gather the dY rows (A), warps 12-15 the X rows (B).  One instruction of a warp moves 16 pair rows x
+    // 2 adjacent 16-byte pieces (lane = (row, piece parity)): every 32-byte L2 sector is fetched whole by one
+    // instruction, and the 16 rows land in 16 distinct 16-byte slots of the core-matrix layout.
+    const int pw = warp - 8;                 // 0..7
+    const bool side_b = pw >= 4;
+    const int j = (pw & 3) * 16 + (lane >> 1);  // pair row inside the stage
+    const int hpar = lane & 1;
     // element (row j, 16-byte chunk c) -> c * (KS * 16) + (j / 8) * 128 + (j % 8) * 16   (per operand / half)
     const uint32_t row_off = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
     int64_t g = 0;
@@ -82,31 +87,22 @@ conv_wgrad_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __re
       const int m0 = (tile / nt) * kWgTile, n0 = (tile % nt) * kWgTile;
       const int4 c4 = chunks[ch];
       const int k_beg = c4.y, k_end = c4.z;
+      const __nv_bfloat16* base = side_b ? X : dY;
+      const int width = side_b ? cin : cout, col0 = side_b ? n0 : m0;
       for (int k0 = k_beg; k0 < k_end; k0 += kWgKS, ++g) {
         const int s = (int)(g % kWgStages);
         const int r = k0 + j;
         const bool ok = r < k_end;
-        const int64_t ro = ok ? pair_out[r] : 0;
-        const int32_t ri = ok ? pair_in[r] : 0;
+        const int64_t row = ok ? (side_b ? (int64_t)pair_in[r] : pair_out[r]) : 0;
         tc::mbar_wait(&empty_bar[s], (uint32_t)((g / kWgStages) & 1) ^ 1);
-        const uint32_t st = tc::smem_u32(smem + s * S::kStageBytes);
-        // A: dY[ro][m0 + 64 q .. +63] -> chunks 8q .. 8q+7 of the 32 (half = chunk / 16)
+        const uint32_t st = tc::smem_u32(smem + s * S::kStageBytes) + (side_b ? (uint32_t)S::kABytes : 0u) + row_off;
+        const __nv_bfloat16* src = base + (size_t)row * width;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int c = q * 8 + u;
-          const int m = m0 + c * 8;
-          const bool v = ok && m < cout;
-          tc::cp_async16(st + (uint32_t)((c >> 4) * (S::kABytes / 2) + (c & 15) * (kWgKS * 16)) + row_off,
-                         dY + (size_t)ro * cout + (v ? m : 0), v ? 16u : 0u);
-        }
-        // B: X[ri][n0 + 64 q .. +63]
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int c = q * 8 + u;
-          const int nn = n0 + c * 8;
-          const bool v = ok && nn < cin;
-          tc::cp_async16(st + (uint32_t)(S::kABytes + c * (kWgKS * 16)) + row_off, X + (size_t)ri * cin + (v ? nn : 0),
-                         v ? 16u : 0u);
+        for (int u = 0; u < 16; ++u) {
+          const int c = 2 * u + hpar;  // chunk 0..31 (A: half = c / 16)
+          const int col = col0 + c * 8;
+          const bool v = ok && col < width;
+          tc::cp_async16(st + (uint32_t)(c * (kWgKS * 16)), src + (v ? col : 0), v ? 16u : 0u);
         }
         tc::cp_async_mbar_arrive_noinc(&full_bar[s]);
       }

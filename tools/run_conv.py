@@ -51,3 +51,20 @@ for tile in (128, 256):
         bb = prod[pairs["ypos"].clamp_min(0).long().flatten()].float()
         m = (ypos128.flatten() >= 0)
         print("   max |tile256 - tile128| over active pairs:", (a[m] - bb[m]).abs().max().item())
+
+# ---- backward kernels at the same shape: dgrad = the forward kernels on mirrored taps, wgrad = csrc/conv_wgrad.cu
+from scenesplat_b200 import training
+pairs = ops.kmap_pairs(nbr, dev(order[0]), 3, cnt.cpu().numpy(), tile=256)
+dy = torch.randn(n, c, device="cuda").bfloat16()
+po = training._pair_out(pairs)
+for _ in range(2):
+    dw = ops.subm_conv_wgrad(x, dy, pairs, po, 27)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    dw = ops.subm_conv_wgrad(x, dy, pairs, po, 27)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(f"n={n} C={c} wgrad: {ms:.3f} ms  {2.0 * pairs['pairs'] * c * c / ms / 1e9:.0f} TFLOP/s useful (incl. zeroing dW)")
