@@ -192,6 +192,9 @@ int ss_lang_head_tc(const void* feat_bf16, const void* text_bf16, int64_t n, int
  * Training path adjoints.  LayerNorm backward (torch nn.LayerNorm in the reference's Block,
  * point_transformer_v3m1_base.py:277-338): dx = d/dx of LN(x; gamma, beta) contracted with dy, in x's dtype;
  * dgamma / dbeta (fp32, [channels]) are ACCUMULATED: zero them first.  channels % 8 == 0, <= 1024. */
+/* GELU (erf form, nn.GELU()) backward on bf16 tensors: dx = dy * (Phi(x) + x phi(x)); n_elements % 8 == 0. */
+int ss_gelu_backward_bf16(const void* x, const void* dy, int64_t n_elements, void* dx, void* stream);
+
 /* Weight gradient of the 3^3 submanifold conv on the tensor cores: dw[t][co][ci] += sum over the pairs r of the K chunks
  * of tap t of dy[pair_out[r]][co] * x[pair_in[r]][ci].  chunks: [n_chunks] int32x4 (tap, k_begin, k_end, 0) over the pair
  * lists of ss_kmap_pairs (exact ranges: padding rows excluded); dw fp32 [k3, cout, cin], ACCUMULATED (zero it first);

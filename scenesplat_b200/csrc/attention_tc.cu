@@ -628,6 +628,9 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
         const int valid = kv_len - j * kKC - half * 64;  // valid keys among this warp's 64 columns (may be <= 0)
         tc::mbar_wait(&s_full[g], s & 1);
         tc::tc_fence_after();
+        [[maybe_unused]] const bool trw = (warp & 7) == 0 && s >= 8 && s < 16;
+        [[maybe_unused]] const int trb = 16 + g * 48 + (s - 8) * 6;
+        if (trw) ATT_TRACE(trb);
         // ---- sweep 1: local row max over the warp's 64 columns
         float mx = -INFINITY;
 #pragma unroll
@@ -649,10 +652,12 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
           }
           mx = fmaxf(mx, fmax3(m0, m1, fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]))));
         }
+        if (trw) ATT_TRACE(trb + 1);
         float* xm = xmax + ((s & 1) * 4 + g * 2) * 128;
         xm[half * 128 + row] = mx;
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         mx = fmaxf(mx, xm[(half ^ 1) * 128 + row]);
+        if (trw) ATT_TRACE(trb + 2);
         const float nm = mx * scale_log2e;  // scale > 0
         const bool need = nm > msc + kLazy;
         if (__any_sync(0xffffffffu, need)) {  // identical in both warps of the pair
@@ -685,6 +690,7 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
             asm volatile("bar.sync 10, 512;" ::: "memory");
           }
         }
+        if (trw) ATT_TRACE(trb + 3);
         const float nmsc = -msc;
 #pragma unroll
         for (int hq = 0; hq < 2; ++hq) {
@@ -711,6 +717,7 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
           }
           tc::tmem_st16(tP + 16 * hq, pk);
         }
+        if (trw) ATT_TRACE(trb + 4);
         if (pp) {
           if (g == 0) {
             if (s < total_other) asm volatile("bar.arrive 10, 512;" ::: "memory");
@@ -721,6 +728,7 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
         tc::tmem_st_wait();
         tc::tc_fence_before();
         tc::mbar_arrive(&p_ready[g]);
+        if (trw) ATT_TRACE(trb + 5);
       }
       // ---- epilogue: this warp writes the column half [half * D/2, (half + 1) * D/2) of its rows
       tc::mbar_wait(&pv_done[g], (s - 1) & 1);

@@ -167,3 +167,43 @@ extern "C" int ss_layernorm_backward(const void* x, int x_is_bf16, const void* d
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
+
+// GELU (erf form) backward: dx = dy * (Phi(x) + x * phi(x)), bf16 in / bf16 out, 8 elements per thread.
+namespace ss {
+__global__ void __launch_bounds__(256)
+gelu_bwd_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    uint4 xv = x[i], gv = dy[i], ov;
+    const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xv);
+    const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 a = __bfloat1622float2(xh[u]), g = __bfloat1622float2(gh[u]);
+      float2 o;
+      {
+        const float cdf = 0.5f * (1.f + erff(a.x * 0.70710678118654752440f));
+        o.x = g.x * (cdf + a.x * 0.3989422804014327f * __expf(-0.5f * a.x * a.x));
+      }
+      {
+        const float cdf = 0.5f * (1.f + erff(a.y * 0.70710678118654752440f));
+        o.y = g.y * (cdf + a.y * 0.3989422804014327f * __expf(-0.5f * a.y * a.y));
+      }
+      oh[u] = __floats2bfloat162_rn(o.x, o.y);
+    }
+    dx[i] = ov;
+  }
+}
+}  // namespace ss
+
+extern "C" int ss_gelu_backward_bf16(const void* x, const void* dy, int64_t n_elements, void* dx, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_elements < 0 || n_elements % 8 != 0) return SS_BAD_ARGS;
+  if (n_elements == 0) return SS_OK;
+  if (!x || !dy || !dx || ((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) % 16 != 0) return SS_BAD_ARGS;
+  const int64_t nvec = n_elements / 8;
+  const int blocks = (int)ss::imin64(ss::ceil_div64(nvec, 256), 32 * ss::kNumSMs);
+  ss::gelu_bwd_bf16x8_kernel<<<blocks, 256, 0, stream>>>((const uint4*)x, (const uint4*)dy, (uint4*)dx, nvec);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}

@@ -310,6 +310,13 @@ def subm_conv_wgrad(x_bf16, dy_bf16, pairs, pair_out, k3, rows_per_chunk=8192):
     return dw
 
 
+def gelu_backward(x_bf16, dy_bf16):
+    x_bf16, dy_bf16 = x_bf16.contiguous(), dy_bf16.contiguous()
+    dx = torch.empty_like(x_bf16)
+    L.call("ss_gelu_backward_bf16", L.ptr(x_bf16), L.ptr(dy_bf16), x_bf16.numel(), L.ptr(dx), L.stream())
+    return dx
+
+
 def layernorm_backward(x, dy, gamma, eps=1e-5):
     """-> (dx in x's dtype, dgamma fp32 [C], dbeta fp32 [C]) of y = LayerNorm(x; gamma, beta) contracted with dy."""
     x, dy = x.contiguous(), dy.contiguous()

@@ -237,6 +237,26 @@ class LayerNormFn(torch.autograd.Function):
         return dx, dg, db, None, None
 
 
+class GeluFn(torch.autograd.Function):
+    """nn.GELU() on the bf16 MLP hidden: the inference path's kernel forward, csrc/backward.cu backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.affine_act(x, act=1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_backward(x, dy.to(BF16))
+
+
+def _gelu(x):
+    if x.dtype == BF16 and x.numel() % 8 == 0:
+        return GeluFn.apply(x.contiguous())
+    return F.gelu(x)
+
+
 def _ln(m: nn.LayerNorm, x, out_dtype=torch.float32):
     c = x.shape[1]
     if c % 8 == 0 and c <= 1024 and x.dtype in (torch.float32, BF16):
@@ -275,11 +295,11 @@ def block_train(blk, point, x, conv_src=None):
     inverse_row = point.serialized_inverse[att.order_index].contiguous()
     a = PatchAttentionFn.apply(qkv, order_row, inverse_row, table, att.patch_size, att.num_heads, att.scale,
                                _patch_plan(point, att.patch_size))
-    x = x + _drop_path(blk.drop_path, _lin(att.proj, a).float())
+    x = x + _drop_path(blk.drop_path, _lin(att.proj, a))
     h = _ln(blk.norm2[0], x, BF16)
     mlp = blk.mlp[0]
-    m = _lin(mlp.fc2, F.gelu(_lin(mlp.fc1, h)))
-    x = x + _drop_path(blk.drop_path, m.float())
+    m = _lin(mlp.fc2, _gelu(_lin(mlp.fc1, h)))
+    x = x + _drop_path(blk.drop_path, m)  # bf16 + fp32 -> fp32 inside the add (no separate cast pass)
     return x
 
 

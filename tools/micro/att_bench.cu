@@ -72,6 +72,15 @@ int main(int argc, char** argv) {
       std::sort(v.begin(), v.end());
       return v[v.size() / 2];
     };
+    if (getenv("ATT_TRACE_WIDE")) {  // 16-softmax-warp kernel: warps 0 (group 0) and 8 (group 1), steps 8..15
+      printf("  step |  g0: S_seen sweep1 exchanged exp_start exps_issued arrived |  g1: ...\n");
+      for (int st = 0; st < 8; ++st) {
+        printf("  %4d |", st + 8);
+        for (int g = 0; g < 2; ++g) { for (int k = 0; k < 6; ++k) printf(" %7lld", med(16 + g * 48 + st * 6 + k, 16)); printf(" |"); }
+        printf("\n");
+      }
+      return 0;
+    }
     for (int s = 1; s < 16; ++s) printf("  %-14s median %8lld clk\n", names[s], med(s, 0));
     printf("  tile transition of group 0 (relative to its last p_ready arrival of tile 0): q_free seen by loader %lld, Q landed %lld, "
            "pv_done seen %lld, epilogue end %lld, q_full seen by MMA %lld, next S seen %lld\n",
