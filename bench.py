@@ -336,7 +336,14 @@ def main():
     ms, prof_hot, launches, clocks = timed(step_resident, args.steps, profile=hot)
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
     # full per-kernel table from a separate instrumented pass (events around ~350 calls/step perturb the step)
-    _, prof, _, _ = timed(step_resident, max(2, args.steps // 2), profile="all", sample=False)
+    # (one chunk at a time: per-call events of two overlapping streams would charge the small index kernels with the
+    # time they spend waiting for SMs behind the feature phase of the previous chunk)
+    def step_sequential():
+        flush.zero_()
+        with torch.no_grad():
+            return model(dict(dev_in))["point_feat"]["feat"]
+
+    _, prof, _, _ = timed(step_sequential, max(2, args.steps // 2), profile="all", sample=False)
     prof_steps = max(2, args.steps // 2)
     total_vox = n_vox
     if world > 1:
@@ -420,8 +427,8 @@ def main():
             gpu_launches=launches, own_kernel_ms_per_step=own_ms, extra_settle_warmup_steps=settle_steps,
             kernels={k: dict(ms_per_step=round(v["ms"] / prof_steps, 4), calls_per_step=v["calls"] / prof_steps)
                      for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])},
-            kernels_note="per-call CUDA-event times from a separate instrumented pass; the roofline kernel is timed "
-                         "inside the timed region itself",
+            kernels_note="per-call CUDA-event times from a separate instrumented, non-pipelined pass; the roofline kernel "
+                         "is timed inside the timed region itself",
             roofline=roofline, serialize_pool_hbm=serialize_pool, cpu_baseline=cpu, clocks=clocks,
         )
         print(json.dumps(line), flush=True)
