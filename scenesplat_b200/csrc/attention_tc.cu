@@ -25,9 +25,18 @@
 // than 2^8 (any shift cancels in O / l; bf16 / fp32 have the exponent range), so O is touched by CUDA cores almost
 // only on the first chunk(s) of a tile.  The kernel is bound by the N*K*H exponentials, not by the tensor pipe
 // (see DESIGN.md); a fraction of them is evaluated on the FMA pipe (exp2_poly).
-#include <cstdlib>
 #include "tc_common.cuh"
 #include "../../include/scenesplat_b200.h"
+
+#ifndef SS_ATT_WIDE
+#define SS_ATT_WIDE 1
+#endif
+#ifndef SS_ATT_POLY
+#define SS_ATT_POLY 3
+#endif
+#ifndef SS_ATT_PP
+#define SS_ATT_PP 1
+#endif
 
 namespace ss {
 
@@ -870,7 +879,7 @@ static int launch_attention16(const void* qkv, const int64_t* order_row, const i
   auto kern = patch_attention_tc16_kernel<D, KMAX, POLY>;
   SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   dim3 grid((unsigned)((size_t)heads * max_patches));
-  static const int pp = getenv("SS_ATT_PP") ? atoi(getenv("SS_ATT_PP")) : 1;  // developer tuning hook
+  constexpr int pp = SS_ATT_PP;
   kern<<<grid, kAtt16Threads, S::kTotal, stream>>>((const __nv_bfloat16*)qkv, order_row, (const int4*)table, heads,
                                                    scale * 1.4426950408889634f, (__nv_bfloat16*)out, pp);
   SS_CHECK_LAUNCH();
@@ -880,7 +889,7 @@ static int launch_attention16(const void* qkv, const int64_t* order_row, const i
 template <int D, int POLY>
 static int launch_attention_var(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches,
                                 int heads, float scale, void* out, cudaStream_t stream) {
-  static const int stagger = getenv("SS_ATT_STAGGER") ? atoi(getenv("SS_ATT_STAGGER")) : 1;  // developer tuning hook
+  constexpr int stagger = 0;  // (a one-time stagger of the two groups does not hold: profiles/r1_attention_ncu.md)
   constexpr int KMAX = 1024;
   using S = AttSmem<D, KMAX>;
   auto kern = patch_attention_tc_kernel<D, KMAX, POLY>;
@@ -893,17 +902,19 @@ static int launch_attention_var(const void* qkv, const int64_t* order_row, const
   return SS_OK;
 }
 
+// Variant selection is a COMPILE-time choice (no environment lookups, no global state in the library):
+//   SS_ATT_WIDE  1 = 16-softmax-warp kernel (default), 0 = 8-softmax-warp kernel
+//   SS_ATT_POLY  exponentials per 8 evaluated on the FMA pipe (default 3)
+//   SS_ATT_PP    group ping-pong of the wide kernel (default 1)
+// tools/micro/att_bench.cu includes this file and can be built with other values for A/B runs.
 template <int D>
 static int launch_attention(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches, int heads,
                             float scale, void* out, cudaStream_t stream) {
-  static const int poly = getenv("SS_ATT_POLY") ? atoi(getenv("SS_ATT_POLY")) : 3;  // developer tuning hooks
-  static const int wide = getenv("SS_ATT_WIDE") ? atoi(getenv("SS_ATT_WIDE")) : 1;  // 16 softmax warps (default)
-  if (wide) {
-    if (poly == 0) return launch_attention16<D, 0>(qkv, order_row, table, max_patches, heads, scale, out, stream);
-    return launch_attention16<D, 3>(qkv, order_row, table, max_patches, heads, scale, out, stream);
-  }
-  if (poly == 0) return launch_attention_var<D, 0>(qkv, order_row, table, max_patches, heads, scale, out, stream);
-  return launch_attention_var<D, 3>(qkv, order_row, table, max_patches, heads, scale, out, stream);
+#if SS_ATT_WIDE
+  return launch_attention16<D, SS_ATT_POLY>(qkv, order_row, table, max_patches, heads, scale, out, stream);
+#else
+  return launch_attention_var<D, SS_ATT_POLY>(qkv, order_row, table, max_patches, heads, scale, out, stream);
+#endif
 }
 
 }  // namespace ss
