@@ -85,7 +85,8 @@ int ss_pool_index(const int64_t* code, const int64_t* order, const int64_t* grid
                   void* stream);
 
 /* torch_scatter.segment_csr(src[order], seg_start, reduce) (+ optional folded-BN affine and GELU).
- * reduce: 0 sum, 1 mean, 2 max, 3 min.  act: 0 none, 1 GELU(erf).  Row count = *m_dev if non-NULL else m. */
+ * reduce: 0 sum, 1 mean, 2 max, 3 min.  act: 0 none, 1 GELU(erf).  Row count = *m_dev if non-NULL else m.
+ * order == NULL: rows in place (plain segment_csr(src, seg_start)); empty segments give 0 like torch_scatter. */
 int ss_segment_reduce(const void* src, int src_is_bf16, const int64_t* order, const int64_t* seg_start,
                       const int64_t* m_dev, int64_t m, int channels, int reduce, const float* scale, const float* shift,
                       int act, void* out, int out_is_bf16, void* stream);

@@ -99,6 +99,7 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
 // One warp per segment (grid-stride).  out[s, :] = reduce_{j in [start[s], start[s+1])} src[order[j], :]
+// (order == nullptr: rows in place, the plain torch_scatter.segment_csr; empty segments give 0 like torch_scatter)
 // then optional per-channel affine (eval-mode BatchNorm folded to scale/shift) and GELU.
 // reduce: 0 = sum, 1 = mean, 2 = max, 3 = min
 template <typename TI, typename TO>
@@ -117,7 +118,7 @@ segment_reduce_kernel(const TI* __restrict__ src, const int64_t* __restrict__ or
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc[u] = reduce == 2 ? -INFINITY : (reduce == 3 ? INFINITY : 0.f);
       for (int64_t j = a; j < b; ++j) {
-        const TI* row = src + (size_t)order[j] * C;
+        const TI* row = src + (size_t)(order ? order[j] : j) * C;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int c = c0 + lane + 32 * u;
@@ -131,8 +132,8 @@ segment_reduce_kernel(const TI* __restrict__ src, const int64_t* __restrict__ or
       for (int u = 0; u < 4; ++u) {
         const int c = c0 + lane + 32 * u;
         if (c < C) {
-          float v = acc[u];
-          if (reduce == 1) v = v / (float)(b - a);
+          float v = b > a ? acc[u] : 0.f;
+          if (reduce == 1 && b > a) v = v / (float)(b - a);
           if (scale) v = v * scale[c] + shift[c];
           if (act == 1) v = gelu_erf(v);
           out[(size_t)s * C + c] = from_f<TO>(v);
@@ -297,7 +298,7 @@ int ss_segment_reduce(const void* src, int src_is_bf16, const int64_t* order, co
   cudaStream_t stream = (cudaStream_t)stream_;
   if (m < 0 || channels < 1 || reduce < 0 || reduce > 3 || (scale && !shift)) return SS_BAD_ARGS;
   if (m == 0) return SS_OK;
-  if (!src || !order || !seg_start || !out) return SS_BAD_ARGS;
+  if (!src || !seg_start || !out) return SS_BAD_ARGS;
   const int blocks = (int)ss::imin64(ss::ceil_div64(m, 8), 16 * ss::kNumSMs);
   if (src_is_bf16 && out_is_bf16)
     ss::segment_reduce_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, stream>>>(

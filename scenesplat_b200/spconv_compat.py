@@ -47,6 +47,17 @@ class SparseConvTensor:
             self._batch_size = int(self._point.batch[-1]) + 1
         return self._batch_size
 
+    def point_view(self):
+        """The Point whose serialized codes index this tensor's voxels.  A tensor built the spconv way
+        (features + [N, 4] (batch, z, y, x) indices, no Point; structure.py:131-138) gets a private z-order view."""
+        if self._point is None:
+            from .structure import Point
+            idx = self._indices
+            p = Point(grid_coord=idx[:, 1:].contiguous(), batch=idx[:, 0].long().contiguous())
+            p.serialization(order=("z",))
+            self._point = p
+        return self._point
+
     def replace_feature(self, feat):
         return SparseConvTensor(feat, self._indices, self._spatial_shape, self._batch_size, self._point, self._pad,
                                 self.indice_dict)
@@ -109,7 +120,7 @@ class SubMConv3d(nn.Module):
         """Convolve `feat` (rows = the Point's voxels).  Optional fused folded-BN affine + activation
         (SIMT path only; used by the stem)."""
         if torch.is_grad_enabled() and (feat.requires_grad or self.weight.requires_grad):
-            raise NotImplementedError("scenesplat_b200: SubMConv3d backward is not built yet (SURVEY.md 8f row 1)")
+            return self._conv_autograd(point, feat, scale, act, out_dtype)
         bias = self.bias.detach().float() if self.bias is not None else None
         if self.tensor_core_ok() and scale is None and act == 0:
             ent = kernel_map_for(point, self.kernel_size, want_pairs=True)
@@ -121,10 +132,26 @@ class SubMConv3d(nn.Module):
         return ops.subm_conv_simt(x, ent["nbr"], self._prepared("simt"), bias, scale, shift, act,
                                   out_dtype=out_dtype or torch.float32)
 
+    def _conv_autograd(self, point, feat, scale, act, out_dtype):
+        """Differentiable path (scenesplat_b200/training.py): tensor-core conv with dgrad / wgrad kernels, or the stem
+        form (tiny Cin, input without gradient)."""
+        from . import training as T
+        if scale is not None or act != 0:
+            raise NotImplementedError("fused affine / activation epilogues are inference-only")
+        if self.tensor_core_ok():
+            ent = kernel_map_for(point, self.kernel_size, want_pairs=True)
+            y = T.SubMConvFn.apply(feat.to(torch.bfloat16), self.weight, self.bias, ent["pairs"], feat.shape[0])
+        elif not feat.requires_grad:
+            ent = kernel_map_for(point, self.kernel_size, want_pairs=False)
+            y = T.StemConvFn.apply(feat.float(), self.weight, ent["nbr"])
+            if self.bias is not None:
+                y = y + self.bias
+        else:
+            raise NotImplementedError("SubMConv3d input gradients need Cin % 16 == 0, Cin >= 32 and Cout % 32 == 0")
+        return y.to(out_dtype) if out_dtype is not None else y
+
     def forward(self, x: SparseConvTensor):
-        if x._point is None:
-            raise NotImplementedError("SubMConv3d needs a SparseConvTensor created by Point.sparsify()")
-        return x.replace_feature(self.conv_point(x._point, x.features, out_dtype=torch.float32))
+        return x.replace_feature(self.conv_point(x.point_view(), x.features, out_dtype=torch.float32))
 
 
 def is_spconv_module(module):

@@ -136,8 +136,11 @@ def _attention_backward(qkv, order_row, inverse_row, plan, K, H, scale, dout):
     directions are gathers), full patches are one batched call on a view, the last patch of an item attends to
     the window of its last K rows and keeps its own tail rows."""
     C = qkv.shape[1] // 3
-    xs = ops.gather_rows(qkv, order_row)        # [n, 3C] sorted
-    dos = ops.gather_rows(dout.contiguous(), order_row)
+    if order_row is None:                        # rows already in sequence order (the flash-attn stand-in)
+        xs, dos = qkv, dout.contiguous()
+    else:
+        xs = ops.gather_rows(qkv, order_row)    # [n, 3C] sorted
+        dos = ops.gather_rows(dout.contiguous(), order_row)
     dxs = torch.zeros_like(xs)
 
     def run(q, k, v, do):
@@ -167,7 +170,7 @@ def _attention_backward(qkv, order_row, inverse_row, plan, K, H, scale, dout):
             dxs[e0 - r:e0, :C] += dq[0]
             dxs[w0:e0, C:2 * C] += dk[0]
             dxs[w0:e0, 2 * C:] += dv[0]
-    return ops.gather_rows(dxs, inverse_row)
+    return dxs if order_row is None else ops.gather_rows(dxs, inverse_row)
 
 
 class PatchAttentionFn(torch.autograd.Function):
