@@ -156,6 +156,22 @@ int ss_patch_attention_simt(const void* qkv, int in_is_bf16, const int64_t* orde
 int ss_patch_attention(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
                        int patch_size, int heads, int head_dim, float scale, void* out_bf16, void* stream);
 
+/* Training forward: the same kernel, additionally writes lse2 [heads, n] fp32 = log2-domain log-sum-exp of the scaled
+ * scores of every query, indexed by SORTED position (lse2[h * n + j]); consumed by ss_patch_attention_backward. */
+int ss_patch_attention_lse(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
+                           int patch_size, int heads, int head_dim, float scale, void* out_bf16, float* lse2, int64_t n,
+                           void* stream);
+
+/* Backward of the patch attention including the adjoints of the order / inverse gathers (autograd of
+ * flash_attn_varlen_qkvpacked_func + the two index ops, point_transformer_v3m1_base.py:181-216):
+ * dqkv [n, 3*H*d] bf16 = d loss / d qkv given dout [n, H*d] bf16, the forward's out and lse2.  tcgen05 kernels
+ * (csrc/attention_bwd.cu); workspace from ss_patch_attention_backward_workspace_bytes. */
+size_t ss_patch_attention_backward_workspace_bytes(int64_t n, int heads, int head_dim);
+int ss_patch_attention_backward(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
+                                const int64_t* order_row, const int32_t* table, int max_patches, int patch_size,
+                                int heads, int head_dim, float scale, int64_t n, void* dqkv_bf16, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Row-wise fusions around the GEMMs of a Block (point_transformer_v3m1_base.py:318-338). */
 

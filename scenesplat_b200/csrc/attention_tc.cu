@@ -26,6 +26,7 @@
 // only on the first chunk(s) of a tile.  The kernel is bound by the N*K*H exponentials, not by the tensor pipe
 // (see DESIGN.md); a fraction of them is evaluated on the FMA pipe (exp2_poly).
 #include "tc_common.cuh"
+#include "attention_math.cuh"
 #include "../../include/scenesplat_b200.h"
 
 #ifndef SS_ATT_WIDE
@@ -73,36 +74,12 @@ struct AttSmem {
   static constexpr int kTotal = kOffOnes + 512 + 128;
 };
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3 minimax
-// polynomial for 2^f (max relative error 7.5e-5, 26x below the bf16 rounding of P), i added into the exponent field.
-// Needs x <= 126; anything below -126 (masked keys: -inf) comes out as 2^-126 * 0.99993 (a denormal: nothing next
-// to the row maximum's weight of >= 2^-8; the clamp keeps the exponent-field addition from borrowing into the sign).
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -126.f);
-  const float t = x + 12582912.f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = x - (t - 12582912.f);
-  float p = fmaf(f, 0.05517166769f, 0.24261112209f);
-  p = fmaf(p, f, 0.69326098571f);
-  p = fmaf(p, f, 0.99992807355f);
-  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float y;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
-  return y;
-}
-
 // POLY: of every 8 exponentials, POLY are evaluated by exp2_poly on the FMA pipe and 8 - POLY by MUFU.EX2
 template <int D, int KMAX, int POLY>
 __global__ void __launch_bounds__(kAttThreads, 1)
 patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ order_row,
                           const int4* __restrict__ table, int H, float scale_log2e, __nv_bfloat16* __restrict__ out,
-                          int stagger_on) {
+                          int stagger_on, float* __restrict__ lse2, int64_t lse_stride) {
   using S = AttSmem<D, KMAX>;
   const int4 e = table[blockIdx.x / H];
   const int q_beg = e.x, n_q = e.y - e.x, kv_beg = e.z, kv_len = e.w - e.z;
@@ -324,6 +301,8 @@ patch_attention_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* 
       const float lsum = __uint_as_float(tc::tmem_ld1(tO + D));  // sum of the bf16 weights, from the tensor core
       tc::tmem_ld_wait();
       const float inv = 1.f / lsum;
+      // training: log2-domain log-sum-exp of the row (scores already scaled), by sorted position, for the backward
+      if (lse2 && out_row >= 0) lse2[(size_t)h * lse_stride + q_beg + qi] = msc + log2f(lsum);
       __nv_bfloat16* orow = out_row >= 0 ? out + (size_t)out_row * C + h * D : nullptr;
 #pragma unroll
       for (int jo = 0; jo < D / 16; ++jo) {
@@ -505,7 +484,7 @@ template <int D, int KMAX, int POLY>
 __global__ void __launch_bounds__(kAtt16Threads, 1)
 patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ order_row,
                             const int4* __restrict__ table, int H, float scale_log2e, __nv_bfloat16* __restrict__ out,
-                            int pingpong) {
+                            int pingpong, float* __restrict__ lse2, int64_t lse_stride) {
   using S = AttSmem<D, KMAX>;
   using S16 = Att16Smem<D, KMAX>;
   const int4 e = table[blockIdx.x / H];
@@ -745,6 +724,7 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
       const float lsum = __uint_as_float(tc::tmem_ld1(tO + D));
       tc::tmem_ld_wait();
       const float inv = 1.f / lsum;
+      if (lse2 && half == 0 && out_row >= 0) lse2[(size_t)h * lse_stride + q_beg + qi] = msc + log2f(lsum);
       __nv_bfloat16* orow = out_row >= 0 ? out + (size_t)out_row * C + h * D + half * (D / 2) : nullptr;
 #pragma unroll
       for (int jo = 0; jo < D / 16; ++jo) {
@@ -873,7 +853,7 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
 
 template <int D, int POLY>
 static int launch_attention16(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches,
-                              int heads, float scale, void* out, cudaStream_t stream) {
+                              int heads, float scale, void* out, float* lse2, int64_t lse_stride, cudaStream_t stream) {
   constexpr int KMAX = 1024;
   using S = Att16Smem<D, KMAX>;
   auto kern = patch_attention_tc16_kernel<D, KMAX, POLY>;
@@ -881,14 +861,14 @@ static int launch_attention16(const void* qkv, const int64_t* order_row, const i
   dim3 grid((unsigned)((size_t)heads * max_patches));
   constexpr int pp = SS_ATT_PP;
   kern<<<grid, kAtt16Threads, S::kTotal, stream>>>((const __nv_bfloat16*)qkv, order_row, (const int4*)table, heads,
-                                                   scale * 1.4426950408889634f, (__nv_bfloat16*)out, pp);
+                                                   scale * 1.4426950408889634f, (__nv_bfloat16*)out, pp, lse2, lse_stride);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
 
 template <int D, int POLY>
 static int launch_attention_var(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches,
-                                int heads, float scale, void* out, cudaStream_t stream) {
+                                int heads, float scale, void* out, float* lse2, int64_t lse_stride, cudaStream_t stream) {
   constexpr int stagger = 0;  // (a one-time stagger of the two groups does not hold: profiles/r1_attention_ncu.md)
   constexpr int KMAX = 1024;
   using S = AttSmem<D, KMAX>;
@@ -897,7 +877,7 @@ static int launch_attention_var(const void* qkv, const int64_t* order_row, const
   // heads fastest: the H CTAs of a patch run together and share the gathered rows' DRAM sectors through L2
   dim3 grid((unsigned)((size_t)heads * max_patches));
   kern<<<grid, kAttThreads, S::kTotal, stream>>>((const __nv_bfloat16*)qkv, order_row, (const int4*)table, heads,
-                                                 scale * 1.4426950408889634f, (__nv_bfloat16*)out, stagger);
+                                                 scale * 1.4426950408889634f, (__nv_bfloat16*)out, stagger, lse2, lse_stride);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
@@ -909,18 +889,19 @@ static int launch_attention_var(const void* qkv, const int64_t* order_row, const
 // tools/micro/att_bench.cu includes this file and can be built with other values for A/B runs.
 template <int D>
 static int launch_attention(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches, int heads,
-                            float scale, void* out, cudaStream_t stream) {
+                            float scale, void* out, float* lse2, int64_t lse_stride, cudaStream_t stream) {
 #if SS_ATT_WIDE
-  return launch_attention16<D, SS_ATT_POLY>(qkv, order_row, table, max_patches, heads, scale, out, stream);
+  return launch_attention16<D, SS_ATT_POLY>(qkv, order_row, table, max_patches, heads, scale, out, lse2, lse_stride, stream);
 #else
-  return launch_attention_var<D, SS_ATT_POLY>(qkv, order_row, table, max_patches, heads, scale, out, stream);
+  return launch_attention_var<D, SS_ATT_POLY>(qkv, order_row, table, max_patches, heads, scale, out, lse2, lse_stride, stream);
 #endif
 }
 
 }  // namespace ss
 
-extern "C" int ss_patch_attention(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
-                                  int patch_size, int heads, int head_dim, float scale, void* out_bf16, void* stream_) {
+static int patch_attention_entry(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
+                                 int patch_size, int heads, int head_dim, float scale, void* out_bf16, float* lse2,
+                                 int64_t lse_stride, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (max_patches < 0 || heads < 1 || patch_size < 1 || patch_size > 1024 || !(scale > 0.f)) return SS_BAD_ARGS;
   if (max_patches == 0) return SS_OK;
@@ -928,9 +909,23 @@ extern "C" int ss_patch_attention(const void* qkv_bf16, const int64_t* order_row
   if (!qkv_bf16 || !order_row || !table || !out_bf16) return SS_BAD_ARGS;
   if (((uintptr_t)qkv_bf16 | (uintptr_t)out_bf16) % 16 != 0) return SS_BAD_ARGS;
   switch (head_dim) {
-    case 16: return ss::launch_attention<16>(qkv_bf16, order_row, table, max_patches, heads, scale, out_bf16, stream);
-    case 32: return ss::launch_attention<32>(qkv_bf16, order_row, table, max_patches, heads, scale, out_bf16, stream);
-    case 48: return ss::launch_attention<48>(qkv_bf16, order_row, table, max_patches, heads, scale, out_bf16, stream);
+    case 16: return ss::launch_attention<16>(qkv_bf16, order_row, table, max_patches, heads, scale, out_bf16, lse2, lse_stride, stream);
+    case 32: return ss::launch_attention<32>(qkv_bf16, order_row, table, max_patches, heads, scale, out_bf16, lse2, lse_stride, stream);
+    case 48: return ss::launch_attention<48>(qkv_bf16, order_row, table, max_patches, heads, scale, out_bf16, lse2, lse_stride, stream);
     default: return SS_BAD_ARGS;
   }
+}
+
+extern "C" int ss_patch_attention(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
+                                  int patch_size, int heads, int head_dim, float scale, void* out_bf16, void* stream_) {
+  return patch_attention_entry(qkv_bf16, order_row, table, max_patches, patch_size, heads, head_dim, scale, out_bf16,
+                               nullptr, 0, stream_);
+}
+
+extern "C" int ss_patch_attention_lse(const void* qkv_bf16, const int64_t* order_row, const int32_t* table,
+                                      int max_patches, int patch_size, int heads, int head_dim, float scale,
+                                      void* out_bf16, float* lse2, int64_t n, void* stream_) {
+  if (!lse2 || n < 0) return SS_BAD_ARGS;
+  return patch_attention_entry(qkv_bf16, order_row, table, max_patches, patch_size, heads, head_dim, scale, out_bf16,
+                               lse2, n, stream_);
 }

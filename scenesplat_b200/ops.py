@@ -272,6 +272,41 @@ def patch_attention(qkv, order_row, table, patch_size: int, heads: int, scale: f
     return out
 
 
+def patch_attention_lse(qkv, order_row, table, patch_size: int, heads: int, scale: float):
+    """Training forward (tcgen05 kernel only): -> (out bf16 [n, C], lse2 fp32 [H, n] by sorted position)."""
+    qkv = qkv.contiguous()
+    n, c3 = qkv.shape
+    c = c3 // 3
+    d = c // heads
+    if not (qkv.dtype == _BF16 and d in (16, 32, 48) and patch_size <= 1024):
+        raise L.CudaKernelError("tcgen05 attention needs bf16 in/out, head_dim in {16,32,48}, patch_size <= 1024")
+    out = torch.empty((n, c), dtype=_BF16, device=qkv.device)
+    lse2 = torch.empty((heads, n), dtype=torch.float32, device=qkv.device)
+    L.call("ss_patch_attention_lse", L.ptr(qkv), L.ptr(order_row), L.ptr(table), table.shape[0], patch_size, heads, d,
+           float(scale), L.ptr(out), L.ptr(lse2), n, L.stream(),
+           meta=dict(flops=4.0 * min(patch_size, n) * c * n, bytes=n * (4.0 * c * 2 + 8),
+                     exps=float(min(patch_size, n)) * n * heads))
+    return out, lse2
+
+
+def patch_attention_backward(qkv, out, dout, lse2, order_row, table, patch_size: int, heads: int, scale: float):
+    """-> d(qkv) bf16 [n, 3C]: tcgen05 backward of the patch attention incl. the order / inverse gather adjoints."""
+    qkv, out, dout = qkv.contiguous(), out.contiguous(), dout.contiguous()
+    n, c3 = qkv.shape
+    c = c3 // 3
+    d = c // heads
+    if not (qkv.dtype == _BF16 and out.dtype == _BF16 and dout.dtype == _BF16 and d in (16, 32, 48) and patch_size <= 1024):
+        raise L.CudaKernelError("tcgen05 attention backward needs bf16 tensors, head_dim in {16,32,48}, patch_size <= 1024")
+    dqkv = torch.empty_like(qkv)
+    nbytes = L.load().ss_patch_attention_backward_workspace_bytes(n, heads, d)
+    ws = L.workspace(nbytes, qkv.device)
+    L.call("ss_patch_attention_backward", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(lse2), L.ptr(order_row),
+           L.ptr(table), table.shape[0], patch_size, heads, d, float(scale), n, L.ptr(dqkv), L.ptr(ws), ws.numel(),
+           L.stream(), meta=dict(flops=14.0 * min(patch_size, n) * c * n, bytes=n * (9.0 * c * 2 + 16 * c),
+                                 exps=2.0 * min(patch_size, n) * n * heads))
+    return dqkv
+
+
 # ------------------------------------------------------------------------------------------- row-wise fusions
 def add_layernorm(res, delta, ln0=None, ln1=None, eps=1e-5, want_res=True, norm_dtype=None, inplace=False):
     """y = res + LN0(delta) (LN0 optional); returns (y fp32 or None, LN1(y) / cast(y) or None)."""

@@ -22,6 +22,8 @@ Indices (serialization, pooling levels, kernel maps, patch tables) carry no grad
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -173,18 +175,34 @@ def _attention_backward(qkv, order_row, inverse_row, plan, K, H, scale, dout):
     return dxs if order_row is None else ops.gather_rows(dxs, inverse_row)
 
 
+ATTN_BACKWARD = os.environ.get("SS_ATTN_BWD", "own")  # developer A/B switch: "sdpa" = library recomputation
+
+
 class PatchAttentionFn(torch.autograd.Function):
+    """Patch attention with the package's tcgen05 kernels in both directions (csrc/attention_tc.cu forward, which
+    also emits the log-sum-exp of every query; csrc/attention_bwd.cu backward)."""
+
     @staticmethod
     def forward(ctx, qkv, order_row, inverse_row, table, K, H, scale, plan):
-        out = ops.patch_attention(qkv, order_row, table, K, H, scale)
-        ctx.save_for_backward(qkv, order_row, inverse_row)
-        ctx.plan, ctx.K, ctx.H, ctx.scale = plan, K, H, scale
+        d = qkv.shape[1] // (3 * H)
+        own = ATTN_BACKWARD == "own" and qkv.dtype == BF16 and d in (16, 32, 48) and K <= 1024
+        if own:
+            out, lse2 = ops.patch_attention_lse(qkv, order_row, table, K, H, scale)
+            ctx.save_for_backward(qkv, order_row, inverse_row, table, out, lse2)
+        else:
+            out = ops.patch_attention(qkv, order_row, table, K, H, scale)
+            ctx.save_for_backward(qkv, order_row, inverse_row)
+        ctx.own, ctx.plan, ctx.K, ctx.H, ctx.scale = own, plan, K, H, scale
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, order_row, inverse_row = ctx.saved_tensors
-        dqkv = _attention_backward(qkv, order_row, inverse_row, ctx.plan, ctx.K, ctx.H, ctx.scale, dout.to(qkv.dtype))
+        if ctx.own:
+            qkv, order_row, inverse_row, table, out, lse2 = ctx.saved_tensors
+            dqkv = ops.patch_attention_backward(qkv, out, dout.to(BF16), lse2, order_row, table, ctx.K, ctx.H, ctx.scale)
+        else:
+            qkv, order_row, inverse_row = ctx.saved_tensors[:3]
+            dqkv = _attention_backward(qkv, order_row, inverse_row, ctx.plan, ctx.K, ctx.H, ctx.scale, dout.to(qkv.dtype))
         return dqkv, None, None, None, None, None, None, None
 
 

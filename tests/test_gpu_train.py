@@ -172,3 +172,51 @@ def test_conv_backward_kernels(c):
     for name, got, want in (("dx", xg.grad, xr.grad), ("dw", wg.grad, wr.grad), ("db", bg.grad, br.grad)):
         rel = ((got.float().cpu() - want).norm() / want.norm()).item()
         assert rel < 1e-2, (name, rel)
+
+
+@pytest.mark.parametrize("H,d,K", [(2, 16, 256), (3, 32, 1024), (2, 48, 1024), (4, 48, 384)])
+def test_patch_attention_backward_kernel(H, d, K):
+    """tcgen05 attention backward (csrc/attention_bwd.cu) vs torch autograd through the fp32 oracle on the same bf16
+    inputs: short item, ragged items (window rule on the last patch), full patches.  Also checks the log-sum-exp the
+    training forward emits.  Tolerance: P, dS and the operands are bf16 (2^-9 relative each), outputs rounded to bf16:
+    cosine > 0.999 and relative L2 < 2e-2 per gradient block (dq, dk, dv)."""
+    from oracle import attention as oattn
+    from scenesplat_b200 import ops
+    rng = np.random.default_rng(3)
+    offset = np.array([K // 2 + 3, K // 2 + 3 + 2 * K + 17, 4 * K + 40 + 333], dtype=np.int64)
+    n, C = int(offset[-1]), H * d
+    torch.manual_seed(0)
+    qkv = (torch.randn(n, 3 * C) * 1.2).bfloat16()
+    dout = torch.randn(n, C).bfloat16()
+    order = np.concatenate([rng.permutation(np.arange(a, b)) for a, b in zip([0, *offset[:-1]], offset)])
+    inverse = np.empty(n, dtype=np.int64)
+    inverse[order] = np.arange(n)
+    scale = d ** -0.5
+    xr = qkv.float().requires_grad_(True)
+    want = oattn.serialized_attention_core(xr, order, inverse, offset, K, H, scale)
+    want.backward(dout.float())
+    table = ops.patch_table(torch.from_numpy(offset).cuda(), K, n)
+    ord_d = torch.from_numpy(order).cuda()
+    out, lse2 = ops.patch_attention_lse(qkv.cuda(), ord_d, table, K, H, scale)
+    # the forward output is unchanged by the extra lse store
+    ref_out = ops.patch_attention(qkv.cuda(), ord_d, table, K, H, scale, impl="tc")
+    assert torch.equal(out, ref_out)
+    # log2-domain log-sum-exp by sorted position, against the oracle's scores
+    pad, unpad, cu = oattn.patch_table(offset, K)
+    q, k, _ = qkv.float().reshape(n, 3, H, d).unbind(1)
+    srt = torch.from_numpy(order[pad])
+    lse_ref = torch.empty(H, len(pad))
+    for s0, e0 in zip(cu[:-1], cu[1:]):
+        sc = torch.einsum("ihd,jhd->hij", q[srt[s0:e0]], k[srt[s0:e0]]) * scale
+        lse_ref[:, s0:e0] = torch.logsumexp(sc, dim=-1) / np.log(2.0)
+    lse_sorted = lse_ref[:, torch.from_numpy(unpad)]  # unpad: sorted position -> padded position of its own query row
+    np.testing.assert_allclose(lse2.cpu().numpy(), lse_sorted.numpy(), atol=2e-2)  # weights are cut to bf16: 2^-8 relative
+    dqkv = ops.patch_attention_backward(qkv.cuda(), out, dout.cuda(), lse2, ord_d, table, K, H, scale)
+    torch.cuda.synchronize()
+    got = dqkv.float().cpu()
+    assert torch.isfinite(got).all()
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        a, b = got[:, sl].flatten(), xr.grad[:, sl].flatten()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        rel = float((a - b).norm() / b.norm())
+        assert cos > 0.999 and rel < 2e-2, f"{name}: cos {cos:.5f} rel {rel:.4f}"
