@@ -212,6 +212,12 @@ int ss_lang_head_tc(const void* feat_bf16, const void* text_bf16, int64_t n, int
 /* GELU (erf form, nn.GELU()) backward on bf16 tensors: dx = dy * (Phi(x) + x phi(x)); n_elements % 8 == 0. */
 int ss_gelu_backward_bf16(const void* x, const void* dy, int64_t n_elements, void* dx, void* stream);
 
+/* out[c] = sum_r x[r, c]: bias gradient of a Linear layer (autograd of F.linear, db = dy.sum(0)), bf16 rows, fp32
+ * deterministic two-stage sum.  channels % 8 == 0. */
+size_t ss_colsum_workspace_bytes(int channels);
+int ss_colsum_bf16(const void* x_bf16, int64_t n, int channels, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
 /* Weight gradient of the 3^3 submanifold conv on the tensor cores: dw[t][co][ci] += sum over the pairs r of the K chunks
  * of tap t of dy[pair_out[r]][co] * x[pair_in[r]][ci].  chunks: [n_chunks] int32x4 (tap, k_begin, k_end, 0) over the pair
  * lists of ss_kmap_pairs (exact ranges: padding rows excluded); dw fp32 [k3, cout, cin], ACCUMULATED (zero it first);

@@ -94,20 +94,34 @@ def _plan_from_cu_seqlens(cu, K):
 
 
 class _VarlenAttnFn(torch.autograd.Function):
+    """tcgen05 forward (with log-sum-exp) and tcgen05 backward; shapes outside the kernels' range (head_dim not in
+    {16, 32, 48} or max_seqlen > 1024) recompute with torch's fused attention."""
+
     @staticmethod
     def forward(ctx, qkv2d, table, cu_seqlens, K, H, scale):
-        out = ops.patch_attention(qkv2d, _arange(qkv2d.shape[0], qkv2d.device), table, K, H, scale)
-        ctx.save_for_backward(qkv2d, cu_seqlens)
+        from .training import _own_attention_backward
+        ident = _arange(qkv2d.shape[0], qkv2d.device)
+        ctx.own = _own_attention_backward(qkv2d.shape[1] // (3 * H), K)
+        if ctx.own:
+            out, lse2 = ops.patch_attention_lse(qkv2d, ident, table, K, H, scale)
+            ctx.save_for_backward(qkv2d, cu_seqlens, table, ident, out, lse2)
+        else:
+            out = ops.patch_attention(qkv2d, ident, table, K, H, scale)
+            ctx.save_for_backward(qkv2d, cu_seqlens)
         ctx.K, ctx.H, ctx.scale = K, H, scale
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        from .training import _attention_backward
-        qkv2d, cu = ctx.saved_tensors
-        plan = _plan_from_cu_seqlens([int(v) for v in cu.cpu().tolist()], ctx.K)
-        return (_attention_backward(qkv2d, None, None, plan, ctx.K, ctx.H, ctx.scale, dout.to(qkv2d.dtype)),
-                None, None, None, None, None)
+        if ctx.own:
+            qkv2d, cu, table, ident, out, lse2 = ctx.saved_tensors
+            dqkv = ops.patch_attention_backward(qkv2d, out, dout.to(qkv2d.dtype), lse2, ident, table, ctx.K, ctx.H, ctx.scale)
+        else:
+            from .training import _attention_backward
+            qkv2d, cu = ctx.saved_tensors
+            plan = _plan_from_cu_seqlens([int(v) for v in cu.cpu().tolist()], ctx.K)
+            dqkv = _attention_backward(qkv2d, None, None, plan, ctx.K, ctx.H, ctx.scale, dout.to(qkv2d.dtype))
+        return dqkv, None, None, None, None, None
 
 
 def _arange(n, device):

@@ -241,13 +241,17 @@ patch_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
         uint32_t pkW[2][16], pkU[2][16];
         tc::mbar_wait(t_full, s & 1);
         tc::tc_fence_after();
+        // column quarter 0 is loaded first; quarter 1's TMEM loads are in flight under quarter 0's arithmetic
+        uint32_t a[2][32], b[2][32];
+        tc::tmem_ld32(tT1, a[0]);
+        tc::tmem_ld32(tT2, b[0]);
+        tc::tmem_ld_wait();
+        tc::tmem_ld32(tT1 + 32, a[1]);
+        tc::tmem_ld32(tT2 + 32, b[1]);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          uint32_t a[32], b[32];
-          tc::tmem_ld32(tT1 + 32 * q, a);
-          tc::tmem_ld32(tT2 + 32 * q, b);
-          tc::tmem_ld_wait();
           if (q == 1) {
+            tc::tmem_ld_wait();
             tc::tc_fence_before();
             tc::mbar_arrive(t_free);  // the next T1 / T2 run under this step's exponentials
           }
@@ -265,9 +269,9 @@ patch_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               const int u = 4 * u4 + v;
-              const float x = fmaf(__uint_as_float(a[u]), scale_log2e, -l[v]);
+              const float x = fmaf(__uint_as_float(a[q][u]), scale_log2e, -l[v]);
               w[v] = (u & 7) < POLY ? exp2_poly(x) : ex2_approx(x);
-              g[v] = w[v] * (__uint_as_float(b[u]) - dl[v]);
+              g[v] = w[v] * (__uint_as_float(b[q][u]) - dl[v]);
             }
             pkW[q][2 * u4] = tc::pack_bf16(w[0], w[1]);
             pkW[q][2 * u4 + 1] = tc::pack_bf16(w[2], w[3]);

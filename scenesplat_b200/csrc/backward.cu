@@ -207,3 +207,81 @@ extern "C" int ss_gelu_backward_bf16(const void* x, const void* dy, int64_t n_el
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
+
+// Column sums of a bf16 matrix (bias gradients of the Linear layers: db = sum_rows dy), fp32 accumulation, deterministic
+// (two stages: per-block partial rows, then one thread per column adds the partials in block order).
+namespace ss {
+constexpr int kColsumCols = 1024;  // columns per blockIdx.y
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, int c, float* __restrict__ partial) {
+  __shared__ float red[8][kColsumCols];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * kColsumCols;
+  const int cw = min(kColsumCols, c - c0);  // columns of this slab (multiple of 8)
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[i][u] = 0.f;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + warp, wn = (int64_t)gridDim.x * 8;
+  for (int64_t r = w0; r < n; r += wn) {
+    const __nv_bfloat16* row = x + (size_t)r * c + c0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = (lane + 32 * i) * 8;
+      if (v < cw) {
+        const uint4 q = *reinterpret_cast<const uint4*>(row + v);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __bfloat1622float2(h[u]);
+          acc[i][2 * u] += f.x;
+          acc[i][2 * u + 1] += f.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) red[warp][(lane + 32 * i) * 8 + u] = acc[i][u];
+  __syncthreads();
+  for (int col = threadIdx.x; col < cw; col += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][col];
+    partial[(size_t)blockIdx.x * c + c0 + col] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= c) return;
+  float t = 0.f;
+  for (int b = 0; b < blocks; ++b) t += partial[(size_t)b * c + col];
+  out[col] = t;
+}
+}  // namespace ss
+
+extern "C" size_t ss_colsum_workspace_bytes(int channels) {
+  return channels < 1 ? 0 : (size_t)2 * ss::kNumSMs * channels * sizeof(float);
+}
+
+extern "C" int ss_colsum_bf16(const void* x, int64_t n, int channels, float* out, void* workspace, size_t workspace_bytes,
+                              void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || channels < 8 || channels % 8 != 0 || !out) return SS_BAD_ARGS;
+  if (n == 0) {
+    SS_CUDA(cudaMemsetAsync(out, 0, (size_t)channels * sizeof(float), stream));
+    return SS_OK;
+  }
+  if (!x || !workspace || ((uintptr_t)x | (uintptr_t)workspace) % 16 != 0) return SS_BAD_ARGS;
+  if (workspace_bytes < ss_colsum_workspace_bytes(channels)) return SS_BAD_ARGS;
+  const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8), 2 * ss::kNumSMs);
+  dim3 grid((unsigned)blocks, (unsigned)((channels + ss::kColsumCols - 1) / ss::kColsumCols));
+  ss::colsum_partial_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, n, channels, (float*)workspace);
+  SS_CHECK_LAUNCH();
+  ss::colsum_final_kernel<<<(channels + 255) / 256, 256, 0, stream>>>((const float*)workspace, blocks, channels, out);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}

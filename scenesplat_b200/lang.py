@@ -92,11 +92,11 @@ class AggregatedContrastiveLoss(nn.Module):
         nc = self.max_classes
         if half is None:
             half, _ = self.random_halves(valid, segment, nc)
-        if pred.requires_grad:
+        if pred.requires_grad:  # training: differentiable and free of host decisions
             from . import training
             sums, counts = training.class_half_sums(pred.float(), valid, segment, half, nc)
-        else:
-            sums, counts = ops.class_half_sums(pred, valid, segment, half, nc)
+            return self.loss_weight * training.contrastive_from_sums(sums, counts, nc, self.temperature, self.reduction)
+        sums, counts = ops.class_half_sums(pred, valid, segment, half, nc)
         per_class = counts.view(nc, 2).sum(1)
         use = (per_class >= 100) & (counts.view(nc, 2).min(1).values > 0)  # losses/misc.py:366-376
         idx = use.nonzero(as_tuple=True)[0]

@@ -189,6 +189,16 @@ def kmap_build(grid_coord, batch, code_row, order_row, depth: int, order_id: int
     return nbr, cnt
 
 
+def upload(values, dtype, device):
+    """Small host table -> device WITHOUT draining the stream: torch.tensor(..., device=cuda) copies from pageable
+    memory and synchronises; a pinned staging buffer with non_blocking=True only enqueues the copy (the pinned block
+    is recycled by torch's host allocator after the copy has run)."""
+    t = torch.tensor(values, dtype=dtype)
+    if torch.device(device).type != "cuda":
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 CONV_TILE = int(os.environ.get("SS_CONV_TILE", "256"))  # rows per gather-GEMM tile (128: first-generation kernel)
 
 
@@ -205,13 +215,13 @@ def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = None):
         tile_tap += [t] * nt
         o += nt * tile
     p_pad = o
-    base_dev = torch.tensor(base, dtype=torch.int64, device=dev)
+    base_dev = upload(base, torch.int64, dev)
     pair_in = torch.empty(max(p_pad, 1), dtype=torch.int32, device=dev)
     ypos = torch.empty((k3, n), dtype=torch.int32, device=dev)
     ws = L.workspace(L.load().ss_kmap_workspace_bytes(n, k), dev)
     L.call("ss_kmap_pairs", L.ptr(nbr), L.ptr(order_row.contiguous()), n, k, L.ptr(base_dev), p_pad, L.ptr(pair_in),
            L.ptr(ypos), L.ptr(ws), ws.numel(), L.stream())
-    return dict(pair_in=pair_in, ypos=ypos, tile_tap=torch.tensor(tile_tap or [0], dtype=torch.int32, device=dev),
+    return dict(pair_in=pair_in, ypos=ypos, tile_tap=upload(tile_tap or [0], torch.int32, dev),
                 p_pad=p_pad, pairs=int(sum(int(c) for c in tap_count_host)), tile=tile, tap_base=list(base),
                 tap_count=[int(c) for c in tap_count_host])
 
@@ -336,7 +346,7 @@ def subm_conv_wgrad(x_bf16, dy_bf16, pairs, pair_out, k3, rows_per_chunk=8192):
         for t, (b0, c) in enumerate(zip(pairs["tap_base"], pairs["tap_count"])):
             for k in range(b0, b0 + c, rows_per_chunk):
                 rows.append((t, k, min(k + rows_per_chunk, b0 + c), 0))
-        pairs[key] = torch.tensor(rows or [(0, 0, 0, 0)], dtype=torch.int32, device=x_bf16.device), len(rows)
+        pairs[key] = upload(rows or [(0, 0, 0, 0)], torch.int32, x_bf16.device), len(rows)
     chunks, n_chunks = pairs[key]
     dw = torch.zeros((k3, cout, cin), dtype=torch.float32, device=x_bf16.device)
     L.call("ss_subm_conv_wgrad", L.ptr(x_bf16.contiguous()), L.ptr(dy_bf16.contiguous()), L.ptr(pairs["pair_in"]),
@@ -350,6 +360,16 @@ def gelu_backward(x_bf16, dy_bf16):
     dx = torch.empty_like(x_bf16)
     L.call("ss_gelu_backward_bf16", L.ptr(x_bf16), L.ptr(dy_bf16), x_bf16.numel(), L.ptr(dx), L.stream())
     return dx
+
+
+def colsum(x_bf16):
+    """-> fp32 [C] = x.sum(0) of a bf16 [N, C] matrix (Linear bias gradient), deterministic."""
+    x_bf16 = x_bf16.contiguous()
+    n, c = x_bf16.shape
+    out = torch.empty(c, dtype=torch.float32, device=x_bf16.device)
+    ws = L.workspace(L.load().ss_colsum_workspace_bytes(c), x_bf16.device)
+    L.call("ss_colsum_bf16", L.ptr(x_bf16), n, c, L.ptr(out), L.ptr(ws), ws.numel(), L.stream())
+    return out
 
 
 def layernorm_backward(x, dy, gamma, eps=1e-5):

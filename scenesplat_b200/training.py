@@ -37,13 +37,16 @@ BF16 = torch.bfloat16
 
 # ------------------------------------------------------------------------------------------------ conv
 def _pair_out(pairs):
-    """Output voxel of every product row (inverse of ypos); padding rows point at voxel 0 and are never used."""
+    """Output voxel of every product row (inverse of ypos); padding rows point at voxel 0 and are never used.
+    Built with one scatter (no nonzero / boolean indexing: those would drain the stream in the middle of the backward)."""
     if "pair_out" not in pairs:
-        ypos = pairs["ypos"]
-        mask = ypos >= 0
-        po = torch.zeros(max(pairs["p_pad"], 1), dtype=torch.long, device=ypos.device)
-        po[ypos[mask].long()] = mask.nonzero()[:, 1]
-        pairs["pair_out"] = po
+        ypos = pairs["ypos"]                      # [k3, n] int32, -1 where the tap has no neighbour
+        k3, n = ypos.shape
+        p_pad = max(pairs["p_pad"], 1)
+        po = torch.zeros(p_pad + 1, dtype=torch.long, device=ypos.device)   # slot p_pad swallows the missing taps
+        idx = torch.where(ypos >= 0, ypos, torch.full_like(ypos, p_pad)).long().reshape(-1)
+        po.scatter_(0, idx, torch.arange(n, device=ypos.device).repeat(k3))
+        pairs["pair_out"] = po[:p_pad].contiguous()
     return pairs["pair_out"]
 
 
@@ -178,14 +181,17 @@ def _attention_backward(qkv, order_row, inverse_row, plan, K, H, scale, dout):
 ATTN_BACKWARD = os.environ.get("SS_ATTN_BWD", "own")  # developer A/B switch: "sdpa" = library recomputation
 
 
+def _own_attention_backward(head_dim, patch_size):
+    return ATTN_BACKWARD == "own" and head_dim in (16, 32, 48) and patch_size <= 1024
+
+
 class PatchAttentionFn(torch.autograd.Function):
     """Patch attention with the package's tcgen05 kernels in both directions (csrc/attention_tc.cu forward, which
     also emits the log-sum-exp of every query; csrc/attention_bwd.cu backward)."""
 
     @staticmethod
     def forward(ctx, qkv, order_row, inverse_row, table, K, H, scale, plan):
-        d = qkv.shape[1] // (3 * H)
-        own = ATTN_BACKWARD == "own" and qkv.dtype == BF16 and d in (16, 32, 48) and K <= 1024
+        own = plan is None
         if own:
             out, lse2 = ops.patch_attention_lse(qkv, order_row, table, K, H, scale)
             ctx.save_for_backward(qkv, order_row, inverse_row, table, out, lse2)
@@ -229,8 +235,48 @@ class SegmentMeanFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------ model walk
+_BF16_PARAMS = {}
+
+
+def _bf16_param(p):
+    """bf16 copy of a parameter, made once per optimiser step (keyed on the tensor's version counter)."""
+    key = id(p)
+    ent = _BF16_PARAMS.get(key)
+    ver = (p._version, p.data_ptr())
+    if ent is None or ent[0] != ver:
+        ent = (ver, p.detach().to(BF16))
+        _BF16_PARAMS[key] = ent
+    return ent[1]
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on bf16 operands (the reference's AMP linears): cuBLASLt GEMMs as in the reference, but with the bf16
+    parameter copies cached per step and the bias gradient from the package's column-sum kernel: 1 + 3 operator
+    dispatches instead of torch's 4 + 9 (three casts, addmm, two mm, a strided reduction, three cast adjoints)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        w16 = _bf16_param(weight)
+        y = F.linear(x, w16, _bf16_param(bias) if bias is not None else None)
+        ctx.save_for_backward(x, w16)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w16 = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ w16 if ctx.needs_input_grad[0] else None
+        dw = dy.t() @ x if ctx.needs_input_grad[1] else None          # bf16 [Cout, Cin]; autograd casts to the parameter dtype
+        db = ops.colsum(dy) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
 def _lin(m: nn.Linear, x):
-    return F.linear(x.to(BF16), m.weight.to(BF16), m.bias.to(BF16) if m.bias is not None else None)
+    x = x.to(BF16)
+    if x.is_cuda and x.dim() == 2 and m.out_features % 8 == 0:
+        return LinearFn.apply(x.contiguous(), m.weight, m.bias)
+    return F.linear(x, m.weight.to(BF16), m.bias.to(BF16) if m.bias is not None else None)
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -314,8 +360,9 @@ def block_train(blk, point, x, conv_src=None):
     table = att.patch_table(point)
     order_row = point.serialized_order[att.order_index].contiguous()
     inverse_row = point.serialized_inverse[att.order_index].contiguous()
-    a = PatchAttentionFn.apply(qkv, order_row, inverse_row, table, att.patch_size, att.num_heads, att.scale,
-                               _patch_plan(point, att.patch_size))
+    own = _own_attention_backward(qkv.shape[1] // (3 * att.num_heads), att.patch_size)
+    plan = None if own else _patch_plan(point, att.patch_size)  # (the library path needs a host copy of the offsets)
+    a = PatchAttentionFn.apply(qkv, order_row, inverse_row, table, att.patch_size, att.num_heads, att.scale, plan)
     x = x + _drop_path(blk.drop_path, _lin(att.proj, a))
     h = _ln(blk.norm2[0], x, BF16)
     mlp = blk.mlp[0]
@@ -400,19 +447,44 @@ def forward_train(model, data_dict):
 
 # ------------------------------------------------------------------------------------------------ losses (autograd)
 def cosine_loss(pred, target, mask, loss_weight=1.0):
-    """losses/misc.py:254-270"""
-    m = mask.bool()
-    if not m.any():
-        return pred.sum() * 0.0
-    return loss_weight * (1.0 - F.cosine_similarity(pred[m].float(), target[m].float(), dim=1, eps=1e-8)).mean()
+    """losses/misc.py:254-270: mean over the valid rows of 1 - cos.  Masked arithmetic over all rows instead of boolean
+    indexing, so nothing synchronises the stream between forward and backward (no valid row -> 0)."""
+    m = mask.reshape(-1).bool()
+    cos = F.cosine_similarity(pred.float(), target.float(), dim=1, eps=1e-8)
+    n_valid = m.sum().clamp(min=1).to(cos.dtype)
+    return loss_weight * (torch.where(m, 1.0 - cos, torch.zeros_like(cos)).sum() / n_valid)
 
 
 def l2_loss(pred, target, mask, loss_weight=1.0):
-    """losses/misc.py:280-295"""
-    m = mask.bool()
-    if not m.any():
-        return pred.sum() * 0.0
-    return loss_weight * ((pred[m].float() - target[m].float()) ** 2).sum(1).mean()
+    """losses/misc.py:280-295: mean over the valid rows of the squared distance (same masking as cosine_loss)."""
+    m = mask.reshape(-1).bool()
+    d2 = ((pred.float() - target.float()) ** 2).sum(1)
+    n_valid = m.sum().clamp(min=1).to(d2.dtype)
+    return loss_weight * (torch.where(m, d2, torch.zeros_like(d2)).sum() / n_valid)
+
+
+def contrastive_from_sums(sums, counts, n_classes, temperature, reduction="mean"):
+    """losses/misc.py:376-412 on the per-(class, half) sums, over a FIXED number of class slots: classes that do not
+    qualify (fewer than 100 points or an empty half) are masked out of the logits and of the mean instead of being
+    removed with nonzero(), so the loss needs no host decision (no qualifying class -> 0)."""
+    c2 = counts.view(n_classes, 2)
+    use = (c2.sum(1) >= 100) & (c2.min(1).values > 0)
+    s = sums.view(n_classes, 2, -1).float()
+    a = F.normalize(s[:, 0], p=2, dim=1)
+    b = F.normalize(s[:, 1], p=2, dim=1)
+    logits = (a @ b.t()) / temperature
+    neg = torch.full_like(logits, -1e30)        # finite: an all-masked row still has a defined softmax gradient
+    n_used = use.sum().clamp(min=1).to(logits.dtype)
+    diag = logits.diagonal()
+
+    def ce(lg):
+        lse = torch.logsumexp(torch.where(use[None, :], lg, neg), dim=1)
+        return torch.where(use, lse - diag, torch.zeros_like(diag)).sum() / n_used
+
+    loss = (ce(logits) + ce(logits.t())) / 2.0
+    if reduction == "sum":
+        loss = loss * use.sum().to(logits.dtype)
+    return loss
 
 
 def class_half_sums(pred, valid, segment, half, n_classes):

@@ -187,3 +187,48 @@ print("OK", len(a))
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("case", ["mixed", "no_valid", "no_class"])
+def test_training_losses_without_host_decisions_match_the_oracle(case):
+    """scenesplat_b200/training.py evaluates the three lang losses with masks instead of boolean indexing / nonzero
+    (nothing synchronises the stream between forward and backward).  Values AND gradients must equal the oracle's
+    restatement of the reference (losses/misc.py:254-421), which removes rows / classes explicitly.  Pure torch: CPU."""
+    from oracle import lang as olang
+    from scenesplat_b200 import training as T
+    g = torch.Generator().manual_seed(11)
+    n, c, nc = 3000, 48, 16
+    pred0 = torch.nn.functional.normalize(torch.randn(n, c, generator=g), dim=1)
+    target = torch.nn.functional.normalize(torch.randn(n, c, generator=g), dim=1)
+    mask = torch.rand(n, generator=g) < 0.7
+    segment = torch.randint(-1, 9, (n,), generator=g)
+    segment[segment == 7] = 8                     # class 7 absent, class 8 present
+    segment[(segment == 3) & (torch.rand(n, generator=g) < 0.9)] = 2   # class 3 left with < 100 points
+    if case == "no_valid":
+        mask = torch.zeros(n, dtype=torch.bool)
+    if case == "no_class":
+        segment = torch.full((n,), -1)
+    half = (torch.rand(n, generator=g) < 0.5).long()
+    valid = mask & (segment != -1)
+
+    def ours(p):
+        sums, counts = T.class_half_sums(p.float(), valid, segment, half, nc)
+        return (T.cosine_loss(p, target, mask, 1.0) + T.l2_loss(p, target, mask, 0.5)
+                + 0.02 * T.contrastive_from_sums(sums, counts, nc, 0.2, "mean"))
+
+    def ref(p):
+        _, A, B = olang.class_half_sums(p, mask, segment, half)
+        return (olang.cosine_loss(p, target, mask, 1.0) + olang.l2_loss(p, target, mask, 0.5)
+                + olang.contrastive_from_sums(A, B, 0.2, 0.02))
+
+    pa, pb = pred0.clone().requires_grad_(True), pred0.clone().requires_grad_(True)
+    la, lb = ours(pa), ref(pb)
+    np.testing.assert_allclose(la.item(), lb.item(), rtol=1e-5, atol=1e-6)
+    la.backward()
+    if lb.requires_grad:
+        lb.backward()
+        want = pb.grad
+    else:
+        want = torch.zeros_like(pred0)
+    assert torch.isfinite(pa.grad).all()
+    np.testing.assert_allclose(pa.grad.numpy(), want.numpy(), rtol=1e-4, atol=1e-7)
