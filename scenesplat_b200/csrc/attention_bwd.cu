@@ -30,6 +30,10 @@
 #include "attention_math.cuh"
 #include "../../include/scenesplat_b200.h"
 
+#ifndef SS_ATTB_POLY
+#define SS_ATTB_POLY 0  // exponentials per 8 evaluated on the FMA pipe (compile-time; measured 0..3: 0 is fastest here)
+#endif
+
 namespace ss {
 
 constexpr int kBwThreads = 384;
@@ -48,6 +52,13 @@ struct AttBwdSmem {
   static constexpr int kOffBar = kOffVec + 2 * KMAX * 4;
   static constexpr int kTotal = kOffBar + 256 + 128;
 };
+
+// 16-byte shared-memory load by 32-bit shared address (the generic pointer would compile to LD.E, not LDS)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -228,6 +239,7 @@ patch_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t tT1 = t_lane + kBwColT1 + 64 * hh, tT2 = t_lane + kBwColT2 + 64 * hh;
     const uint32_t tW = t_lane + kBwColW + 32 * hh, tU = t_lane + kBwColU + 32 * hh;
+    const uint32_t sL_addr = tc::smem_u32(sL);
     int s = 0;
     for (int i = 0; i < nlt; ++i) {
       const int li = i * kBwT + row;
@@ -255,13 +267,12 @@ patch_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
             tc::tc_fence_before();
             tc::mbar_arrive(t_free);  // the next T1 / T2 run under this step's exponentials
           }
-          const float4* L4 = reinterpret_cast<const float4*>(sL + j * kBwT + 64 * hh + 32 * q);
-          const float4* D4 = reinterpret_cast<const float4*>(sD + j * kBwT + 64 * hh + 32 * q);
+          const uint32_t aL = sL_addr + (uint32_t)(j * kBwT + 64 * hh + 32 * q) * 4u, aD = aL + KMAX * 4u;
 #pragma unroll
           for (int u4 = 0; u4 < 8; ++u4) {
             float l[4] = {lrow, lrow, lrow, lrow}, dl[4] = {drow, drow, drow, drow};
             if (MODE == 1) {  // same address in every lane: shared-memory broadcast
-              const float4 lv = L4[u4], dv = D4[u4];
+              const float4 lv = lds128(aL + 16 * u4), dv = lds128(aD + 16 * u4);
               l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
               dl[0] = dv.x; dl[1] = dv.y; dl[2] = dv.z; dl[3] = dv.w;
             }
@@ -460,7 +471,7 @@ static int launch_attention_bwd(const void* qkv, const void* dout, const float* 
                                 void* dqkv, float* dkv32, cudaStream_t stream) {
   constexpr int KMAX = 1024;
   using S = AttBwdSmem<D, KMAX>;
-  auto kern = patch_attention_bwd_kernel<D, KMAX, MODE, 3>;
+  auto kern = patch_attention_bwd_kernel<D, KMAX, MODE, SS_ATTB_POLY>;
   SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   dim3 grid((unsigned)((size_t)heads * max_patches));  // heads fastest: the H CTAs of a patch share rows through L2
   kern<<<grid, kBwThreads, S::kTotal, stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, lse2, delta, n,
