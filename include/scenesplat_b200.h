@@ -123,6 +123,13 @@ int ss_subm_conv_simt(const void* in, int in_is_bf16, const int32_t* nbr, const 
                       const float* scale, const float* shift, int act, int64_t n, int k3, int cin, int cout, void* out,
                       int out_is_bf16, void* stream);
 
+/* Training: weight gradient of a stem-like conv (fp32, Cout == 32, k^3 * Cin <= 1536):
+ * dw[t][ci][co] = sum_p in[nbr[t][p]][ci] * dy[p][co]  (the [k^3, cin, cout] layout of ss_subm_conv_simt's wt).
+ * Autograd of spconv.SubMConv3d(11 -> 32, k = 5) w.r.t. the weight (point_transformer_v3m1_base.py:499-506). */
+size_t ss_stem_conv_wgrad_workspace_bytes(int k3, int cin);
+int ss_stem_conv_wgrad(const float* in, const float* dy, const int32_t* nbr, int64_t n, int k3, int cin, int cout,
+                       float* dw, void* workspace, size_t workspace_bytes, void* stream);
+
 /* tcgen05 gather-GEMM: prod[r, :] = in[pair_in[r], :] @ w[tap(r)]^T for r < p_pad (bf16 in, fp32
  * accumulate in TMEM, bf16 out).  w is [k^3, cout, cin] bf16 (K-major), tile_tap_host [p_pad/128]
  * int32 gives the tap of every 128-row tile.  cin, cout multiples of 16 (cout <= 768...). */

@@ -362,6 +362,18 @@ def gelu_backward(x_bf16, dy_bf16):
     return dx
 
 
+def stem_conv_wgrad(x_f32, dy_f32, nbr, k3):
+    """-> dw fp32 [k3, cin, 32] of the stem conv (tiny Cin, Cout = 32), deterministic."""
+    x_f32, dy_f32 = x_f32.contiguous(), dy_f32.contiguous()
+    n, cin = x_f32.shape
+    cout = dy_f32.shape[1]
+    dw = torch.empty((k3, cin, cout), dtype=torch.float32, device=x_f32.device)
+    ws = L.workspace(L.load().ss_stem_conv_wgrad_workspace_bytes(k3, cin), x_f32.device)
+    L.call("ss_stem_conv_wgrad", L.ptr(x_f32), L.ptr(dy_f32), L.ptr(nbr), n, k3, cin, cout, L.ptr(dw), L.ptr(ws), ws.numel(),
+           L.stream())
+    return dw
+
+
 def colsum(x_bf16):
     """-> fp32 [C] = x.sum(0) of a bf16 [N, C] matrix (Linear bias gradient), deterministic."""
     x_bf16 = x_bf16.contiguous()

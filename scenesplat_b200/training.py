@@ -103,6 +103,9 @@ class StemConvFn(torch.autograd.Function):
         k3 = weight.numel() // (cout * cin)
         dy = dy.float()
         n = x.shape[0]
+        if cout == 32 and k3 * cin <= 1536 and x.dtype == torch.float32:  # csrc/conv_simt.cu: stem_wgrad kernels
+            dw = ops.stem_conv_wgrad(x, dy, nbr, k3)                        # [k3, cin, cout]
+            return None, dw.permute(2, 0, 1).reshape(weight.shape).to(weight.dtype), None
         xp = torch.cat([x.float(), x.new_zeros(1, cin, dtype=torch.float32)], 0)
         idx = torch.where(nbr >= 0, nbr, torch.full_like(nbr, n)).long()  # [k3, n]; missing neighbour -> the zero row
         dw = torch.matmul(xp[idx].transpose(1, 2), dy)                      # [k3, cin, n] @ [n, cout]

@@ -251,3 +251,31 @@ def test_colsum_kernel_and_linear_fn(n, c):
             assert a.dtype == b.dtype and a.shape == b.shape, name
             # dx / dW: identical cuBLASLt GEMMs; db: fp32 column sum vs torch's bf16-rounded reduction
             np.testing.assert_allclose(a.float().cpu().numpy(), b.float().cpu().numpy(), rtol=1e-2, atol=1e-2 * float(b.float().abs().max()))
+
+
+def test_stem_conv_wgrad_kernel():
+    """csrc/conv_simt.cu stem weight gradient vs the gathered batched matmul in float64 (fp32 kernel: 1e-4 relative to
+    the largest entry), bit-identical between runs (deterministic two-stage sum)."""
+    from oracle import gridsample as ogs
+    from oracle import serialization as oser
+    from scenesplat_b200 import ops, synthetic
+    d = synthetic.chunk(9000, L=3.0, H=2.0, seed=4)
+    g = ogs.grid_sample_train(d["coord"], 0.02)["grid_coord"]
+    n = g.shape[0]
+    offset = np.array([n // 2, n], dtype=np.int64)
+    batch = oser.offset2batch(offset)
+    code, order, inv, depth = oser.serialization(g, batch, 2, oser.ORDERS)
+    k, cin, cout = 5, 11, 32
+    nbr, _ = ops.kmap_build(torch.from_numpy(g).cuda(), torch.from_numpy(batch).cuda(), torch.from_numpy(code[0]).cuda(),
+                            torch.from_numpy(order[0]).cuda(), depth, 0, k)
+    torch.manual_seed(0)
+    x = torch.randn(n, cin)
+    dy = torch.randn(n, cout)
+    got = ops.stem_conv_wgrad(x.cuda(), dy.cuda(), nbr, k ** 3)
+    assert torch.equal(got, ops.stem_conv_wgrad(x.cuda(), dy.cuda(), nbr, k ** 3))
+    nb = nbr.cpu().long()
+    xp = torch.cat([x.double(), torch.zeros(1, cin, dtype=torch.float64)], 0)
+    idx = torch.where(nb >= 0, nb, torch.full_like(nb, n))
+    want = torch.matmul(xp[idx].transpose(1, 2), dy.double())  # [k3, cin, cout]
+    err = (got.cpu().double() - want).abs().max()
+    assert err <= 1e-4 * want.abs().max(), float(err)
