@@ -23,9 +23,11 @@
 // 128 x 128 tile), 8 / 11 loaders of X1 / X2 (next tile prefetched into registers), 9 MMA issuer, 10 vectors (mode 1).
 // TMEM columns: T1 [0,128) T2 [128,256) | W [256,320) U [320,384) (bf16 pairs) | acc1 [384,448) acc2 [448,512).
 // The next T1 / T2 are issued as soon as the current ones are in registers, i.e. they run under the exponentials.
-// dQ rows are written straight to d(qkv) (every query belongs to one patch); dK / dV rows are added into an fp32
-// scratch with vector reductions (the window of an item's last patch shares keys with the patch before it: two
-// addends per element, so the sum does not depend on the order) and converted by a last small kernel.
+// dQ rows are written straight to d(qkv) (every query belongs to one patch), and so are the dK / dV rows of keys only
+// one patch attends to.  The window of an item's last patch shares K - r keys with the patch before it: those rows are
+// added into a zeroed fp32 scratch with vector reductions (two addends per element, so the sum does not depend on
+// the order) and converted by a last small kernel (attn_shared_rows_kernel).  Tables other than ss_patch_table's
+// must keep that convention: kv ranges overlap only as [kv_begin, q_begin) of an entry with the entry before it.
 #include "tc_common.cuh"
 #include "attention_math.cuh"
 #include "../../include/scenesplat_b200.h"
@@ -89,22 +91,35 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __
   delta[(size_t)h * n + pos] = acc;
 }
 
-// dqkv[r, C + c] = bf16(dkv32[r, c]),  c < 2C
+// Keys that two patches attend to (the window of an item's last patch reaches K - r rows back into the patch before
+// it: sorted positions [kv_begin, q_begin) of every table entry with kv_begin < q_begin) get their dK / dV from two
+// CTAs.  Only those rows go through the fp32 scratch: STORE = 0 zeroes them before the backward kernels, STORE = 1
+// converts the sums into d(qkv) afterwards.  grid = (max_patches, 8 row slices).
+template <int STORE>
 __global__ void __launch_bounds__(256)
-attn_dkv_store_kernel(const float* __restrict__ dkv32, int64_t n, int C, __nv_bfloat16* __restrict__ dqkv) {
+attn_shared_rows_kernel(const int4* __restrict__ table, const int64_t* __restrict__ order_row, int C,
+                        float* __restrict__ dkv32, __nv_bfloat16* __restrict__ dqkv) {
+  const int4 e = table[blockIdx.x];
+  if (e.y <= e.x || e.z >= e.x) return;  // unused entry / nothing borrowed
   const int per_row = 2 * C / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * per_row) return;
-  const int64_t r = idx / per_row;
-  const int c = (int)(idx - r * per_row) * 8;
-  const float4 a = *reinterpret_cast<const float4*>(dkv32 + (size_t)r * 2 * C + c);
-  const float4 b = *reinterpret_cast<const float4*>(dkv32 + (size_t)r * 2 * C + c + 4);
-  uint4 o;
-  o.x = tc::pack_bf16(a.x, a.y);
-  o.y = tc::pack_bf16(a.z, a.w);
-  o.z = tc::pack_bf16(b.x, b.y);
-  o.w = tc::pack_bf16(b.z, b.w);
-  *reinterpret_cast<uint4*>(dqkv + (size_t)r * 3 * C + C + c) = o;
+  for (int pos = e.z + blockIdx.y; pos < e.x; pos += gridDim.y) {
+    const size_t r = (size_t)order_row[pos];
+    for (int v = threadIdx.x; v < per_row; v += 256) {
+      float4* src = reinterpret_cast<float4*>(dkv32 + r * 2 * C + v * 8);
+      if (STORE) {
+        const float4 a = src[0], b = src[1];
+        uint4 o;
+        o.x = tc::pack_bf16(a.x, a.y);
+        o.y = tc::pack_bf16(a.z, a.w);
+        o.z = tc::pack_bf16(b.x, b.y);
+        o.w = tc::pack_bf16(b.z, b.w);
+        *reinterpret_cast<uint4*>(dqkv + r * 3 * C + C + v * 8) = o;
+      } else {
+        src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
 }
 
 // POLY: of every 8 exponentials, POLY are evaluated on the FMA pipe (exp2_poly), the rest by MUFU.EX2
@@ -112,12 +127,19 @@ template <int D, int KMAX, int MODE, int POLY>
 __global__ void __launch_bounds__(kBwThreads, 1)
 patch_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                            const float* __restrict__ lse2, const float* __restrict__ delta, int64_t vec_stride,
-                           const int64_t* __restrict__ order_row, const int4* __restrict__ table, int H, float scale,
-                           float scale_log2e, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dkv32) {
+                           const int64_t* __restrict__ order_row, const int4* __restrict__ table, int n_patches, int H,
+                           float scale, float scale_log2e, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dkv32) {
   using S = AttBwdSmem<D, KMAX>;
   const int4 e = table[blockIdx.x / H];
   const int q_beg = e.x, n_q = e.y - e.x, kv_beg = e.z, kv_len = e.w - e.z;
   if (n_q <= 0) return;  // block-uniform: unused table entry
+  // first sorted position of this patch's keys that the NEXT table entry's window borrows (ss_patch_table puts an
+  // item's last patch right after the patch it borrows from); INT_MAX if none
+  int lend_beg = 0x7fffffff;
+  if (MODE == 1 && (int)(blockIdx.x / H) + 1 < n_patches) {
+    const int4 nx = table[blockIdx.x / H + 1];
+    if (nx.y > nx.x && nx.z < nx.x && nx.z >= e.z && nx.z < e.w) lend_beg = nx.z;
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   uint64_t* bars = (uint64_t*)(smem + S::kOffBar);
@@ -332,20 +354,40 @@ patch_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
           }
         }
       } else {
-        // column half 0: dK = scale * acc2, column half 1: dV = acc1; added into the fp32 scratch [n, 2C] (K | V)
+        // column half 0: dK = scale * acc2, column half 1: dV = acc1.  A key that only this patch attends to is
+        // written straight to d(qkv) as bf16; a key shared with the neighbouring patch (borrowed by this patch's
+        // window, or lent to the next entry's window) is added into the zeroed fp32 scratch [n, 2C] (K | V)
         const float f = hh == 0 ? scale : 1.f;
         const uint32_t tA = t_lane + (hh == 0 ? kBwColA2 : kBwColA1);
-        float* dst = orow >= 0 ? dkv32 + (size_t)orow * (2 * C) + (hh == 0 ? 0 : C) + h * D : nullptr;
+        const int pos = l_beg + li;
+        const bool shared_row = pos < q_beg || pos >= lend_beg;
+        float* dst32 = orow >= 0 ? dkv32 + (size_t)orow * (2 * C) + (hh == 0 ? 0 : C) + h * D : nullptr;
+        __nv_bfloat16* dst16 = orow >= 0 ? dqkv + (size_t)orow * (3 * C) + (hh == 0 ? C : 2 * C) + h * D : nullptr;
 #pragma unroll
         for (int jo = 0; jo < D / 16; ++jo) {
           uint32_t o[16];
           tc::tmem_ld16(tA + jo * 16, o);
           tc::tmem_ld_wait();
-          if (dst) {
+          if (orow >= 0) {
+            if (shared_row) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-              red_add_v4(dst + jo * 16 + 4 * v, __uint_as_float(o[4 * v]) * f, __uint_as_float(o[4 * v + 1]) * f,
-                         __uint_as_float(o[4 * v + 2]) * f, __uint_as_float(o[4 * v + 3]) * f);
+              for (int v = 0; v < 4; ++v)
+                red_add_v4(dst32 + jo * 16 + 4 * v, __uint_as_float(o[4 * v]) * f, __uint_as_float(o[4 * v + 1]) * f,
+                           __uint_as_float(o[4 * v + 2]) * f, __uint_as_float(o[4 * v + 3]) * f);
+            } else {
+              uint4 o0, o1;
+              o0.x = tc::pack_bf16(__uint_as_float(o[0]) * f, __uint_as_float(o[1]) * f);
+              o0.y = tc::pack_bf16(__uint_as_float(o[2]) * f, __uint_as_float(o[3]) * f);
+              o0.z = tc::pack_bf16(__uint_as_float(o[4]) * f, __uint_as_float(o[5]) * f);
+              o0.w = tc::pack_bf16(__uint_as_float(o[6]) * f, __uint_as_float(o[7]) * f);
+              o1.x = tc::pack_bf16(__uint_as_float(o[8]) * f, __uint_as_float(o[9]) * f);
+              o1.y = tc::pack_bf16(__uint_as_float(o[10]) * f, __uint_as_float(o[11]) * f);
+              o1.z = tc::pack_bf16(__uint_as_float(o[12]) * f, __uint_as_float(o[13]) * f);
+              o1.w = tc::pack_bf16(__uint_as_float(o[14]) * f, __uint_as_float(o[15]) * f);
+              uint4* d4 = reinterpret_cast<uint4*>(dst16 + jo * 16);
+              d4[0] = o0;
+              d4[1] = o1;
+            }
           }
         }
       }
@@ -475,7 +517,7 @@ static int launch_attention_bwd(const void* qkv, const void* dout, const float* 
   SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   dim3 grid((unsigned)((size_t)heads * max_patches));  // heads fastest: the H CTAs of a patch share rows through L2
   kern<<<grid, kBwThreads, S::kTotal, stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, lse2, delta, n,
-                                                order_row, (const int4*)table, heads, scale,
+                                                order_row, (const int4*)table, max_patches, heads, scale,
                                                 scale * 1.4426950408889634f, (__nv_bfloat16*)dqkv, dkv32);
   SS_CHECK_LAUNCH();
   return SS_OK;
@@ -486,7 +528,9 @@ static int attention_bwd_all(const void* qkv, const void* out, const void* dout,
                              const int64_t* order_row, const int32_t* table, int max_patches, int heads, float scale,
                              float* delta, float* dkv32, void* dqkv, cudaStream_t stream) {
   const int C = heads * D;
-  SS_CUDA(cudaMemsetAsync(dkv32, 0, (size_t)n * 2 * C * sizeof(float), stream));
+  dim3 sgrid((unsigned)max_patches, 8);
+  attn_shared_rows_kernel<0><<<sgrid, 256, 0, stream>>>((const int4*)table, order_row, C, dkv32, (__nv_bfloat16*)dqkv);
+  SS_CHECK_LAUNCH();
   const int64_t nd = n * heads;
   attn_delta_kernel<<<(unsigned)ceil_div64(nd, 256), 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout,
                                                                        order_row, n, heads, D, delta);
@@ -495,8 +539,7 @@ static int attention_bwd_all(const void* qkv, const void* out, const void* dout,
   if (rc) return rc;
   rc = launch_attention_bwd<D, 1>(qkv, dout, lse2, delta, n, order_row, table, max_patches, heads, scale, dqkv, dkv32, stream);
   if (rc) return rc;
-  const int64_t ns = n * (2 * C / 8);
-  attn_dkv_store_kernel<<<(unsigned)ceil_div64(ns, 256), 256, 0, stream>>>(dkv32, n, C, (__nv_bfloat16*)dqkv);
+  attn_shared_rows_kernel<1><<<sgrid, 256, 0, stream>>>((const int4*)table, order_row, C, dkv32, (__nv_bfloat16*)dqkv);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
