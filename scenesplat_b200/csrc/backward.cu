@@ -224,20 +224,30 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, int c, flo
 #pragma unroll
     for (int u = 0; u < 8; ++u) acc[i][u] = 0.f;
   const int64_t w0 = (int64_t)blockIdx.x * 8 + warp, wn = (int64_t)gridDim.x * 8;
-  for (int64_t r = w0; r < n; r += wn) {
-    const __nv_bfloat16* row = x + (size_t)r * c + c0;
+  // two rows per iteration: 8 independent 16-byte loads in flight per lane
+  for (int64_t r = w0; r < n; r += 2 * wn) {
+    const __nv_bfloat16* row0 = x + (size_t)r * c + c0;
+    const bool two = r + wn < n;
+    const __nv_bfloat16* row1 = two ? row0 + (size_t)wn * c : row0;
+    uint4 q0[4], q1[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int v = (lane + 32 * i) * 8;
+      q0[i] = q1[i] = make_uint4(0u, 0u, 0u, 0u);  // bf16 zeros
       if (v < cw) {
-        const uint4 q = *reinterpret_cast<const uint4*>(row + v);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+        q0[i] = *reinterpret_cast<const uint4*>(row0 + v);
+        if (two) q1[i] = *reinterpret_cast<const uint4*>(row1 + v);
+      }
+    }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float2 f = __bfloat1622float2(h[u]);
-          acc[i][2 * u] += f.x;
-          acc[i][2 * u + 1] += f.y;
-        }
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&q0[i]);
+      const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&q1[i]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f0 = __bfloat1622float2(h0[u]), f1 = __bfloat1622float2(h1[u]);
+        acc[i][2 * u] += f0.x + f1.x;
+        acc[i][2 * u + 1] += f0.y + f1.y;
       }
     }
   }
