@@ -93,6 +93,25 @@ def linear_bf16(lin: nn.Linear, x):
     return y
 
 
+def cpe_folded(conv, lin: nn.Linear):
+    """xCPE conv followed by its Linear (ref :277-287) as ONE conv: Linear(b_c + sum_t W_t x_t) =
+    (W_l b_c + b_l) + sum_t (W_l W_t) x_t.  The composed per-tap weights [k^3, C_out, C_in] are formed once in fp32
+    (eval: the parameters are constants) and rounded to bf16; the C x C GEMM over all N voxels and the bf16 round trip
+    of the conv output disappear from every Block."""
+    def fn():
+        cout, cin = conv.out_channels, conv.in_channels
+        k3 = conv.kernel_size ** 3
+        wc = conv.weight.detach().float().reshape(cout, k3, cin).permute(1, 0, 2)       # [k3, cout, cin]
+        wl = lin.weight.detach().float()                                                # [C, cout]
+        w = torch.matmul(wl.unsqueeze(0), wc).to(BF16).contiguous()                    # [k3, C, cin]
+        b = lin.bias.detach().float() if lin.bias is not None else torch.zeros(lin.out_features, device=wl.device)
+        if conv.bias is not None:
+            b = b + wl @ conv.bias.detach().float()
+        return w, b.contiguous()
+    deps = [conv.weight, lin.weight] + [t for t in (conv.bias, lin.bias) if t is not None]
+    return _cache.get(("cpe", id(conv), id(lin)), deps, fn)
+
+
 def ln_params(ln: nn.LayerNorm):
     return _cache.get(("ln", id(ln)), [ln.weight, ln.bias],
                       lambda: (ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous()))
@@ -265,8 +284,13 @@ class Block(PointModule):
         # xCPE: the conv reads sparse_conv_feat.features (modules.py:68-72), which after an unpooling is the
         # skip projection only (reference quirk, see oracle/ptv3.py: unpooling_forward)
         src = point.sparse_conv_feat.features
-        y = conv.conv_point(point, _bf16_of(point, src))
-        z = linear_bf16(cpe_lin, y)
+        if conv.tensor_core_ok() and cpe_lin.out_features % 32 == 0:
+            w_fold, b_fold = cpe_folded(conv, cpe_lin)  # conv and Linear composed into one tensor-core conv
+            ent = spconv.kernel_map_for(point, conv.kernel_size, want_pairs=True)
+            z = ops.subm_conv_gemm(_bf16_of(point, src), ent["pairs"], w_fold, b_fold, x.shape[0], out_dtype=BF16)
+        else:
+            y = conv.conv_point(point, _bf16_of(point, src))
+            z = linear_bf16(cpe_lin, y)
         x, h = ops.add_layernorm(x, z, ln_params(cpe_ln), ln_params(self.norm1[0]), cpe_ln.eps, norm_dtype=BF16)
         qkv = linear_bf16(self.attn.qkv, h)
         a = self.attn.core(point, qkv)

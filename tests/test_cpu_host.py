@@ -232,3 +232,34 @@ def test_training_losses_without_host_decisions_match_the_oracle(case):
         want = torch.zeros_like(pred0)
     assert torch.isfinite(pa.grad).all()
     np.testing.assert_allclose(pa.grad.numpy(), want.numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_cpe_conv_linear_folding_is_the_same_function():
+    """ptv3.cpe_folded composes the xCPE conv with its Linear into per-tap weights (inference).  Against the oracle's
+    fp32 conv followed by the Linear on the same inputs: identical up to the bf16 rounding of the composed weights
+    (2^-9 relative per weight -> < 1e-2 relative L2 of the output).  Pure torch on the CPU."""
+    from oracle import gridsample as ogs
+    from oracle import subm_conv as oconv
+    from scenesplat_b200 import ptv3, synthetic
+    from scenesplat_b200.spconv_compat import SubMConv3d
+    d = synthetic.chunk(3000, L=2.0, H=1.5, seed=3)
+    g = ogs.grid_sample_train(d["coord"], 0.04)["grid_coord"]
+    n, c = g.shape[0], 32
+    torch.manual_seed(0)
+    conv = SubMConv3d(c, c, kernel_size=3, bias=True)
+    lin = torch.nn.Linear(c, c)
+    x = torch.randn(n, c)
+    nbr = oconv.kernel_map(g, np.zeros(n, dtype=np.int64), 3)
+    with torch.no_grad():
+        want = lin(oconv.subm_conv(x, nbr, conv.weight, conv.bias))
+        w, b = ptv3.cpe_folded(conv, lin)                       # [k3, C, C] bf16, [C] fp32
+        assert w.shape == (27, c, c) and w.dtype == torch.bfloat16 and b.dtype == torch.float32
+        w5 = w.float().permute(1, 0, 2).reshape(c, 3, 3, 3, c)  # back to the conv layout [Cout, k, k, k, Cin]
+        got = oconv.subm_conv(x, nbr, w5, b)
+    rel = float((got - want).norm() / want.norm())
+    assert rel < 1e-2, rel
+    # the cache follows parameter updates
+    with torch.no_grad():
+        lin.weight.mul_(2.0)
+    w2, _ = ptv3.cpe_folded(conv, lin)
+    assert not torch.equal(w2, w)
