@@ -13,6 +13,7 @@ from .lang import (AggregatedContrastiveLoss, ChunkPipeline, CosineSimilarity, C
 from .transform import GridSample, SphereCrop  # noqa: F401
 from .voting import confusion_update, neighbor_voting  # noqa: F401
 from .spconv_compat import SparseConvTensor, SubMConv3d  # noqa: F401
+from . import scene_io  # noqa: F401  (packed scene files: pack_scene / load_scene)
 from . import compat  # noqa: F401  (torch_scatter / flash_attn / spconv stand-ins: compat.install())
 
 __version__ = "0.1.0"

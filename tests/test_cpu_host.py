@@ -263,3 +263,51 @@ def test_cpe_conv_linear_folding_is_the_same_function():
         lin.weight.mul_(2.0)
     w2, _ = ptv3.cpe_folded(conv, lin)
     assert not torch.equal(w2, w)
+
+
+def _write_scene_folder(path, n=5000, seed=0, with_segment=True):
+    rng = np.random.default_rng(seed)
+    os.makedirs(path, exist_ok=True)
+    arrays = dict(coord=rng.random((n, 3)) * 5,                       # float64 on disk: get_data casts
+                  color=rng.integers(0, 256, (n, 3)).astype(np.uint8), opacity=rng.random(n).astype(np.float32),
+                  quat=rng.standard_normal((n, 4)).astype(np.float32), scale=(rng.random((n, 3)) * 3).astype(np.float32),
+                  lang_feat=rng.standard_normal((n, 768)).astype(np.float16), valid_feat_mask=(rng.random(n) < 0.8).astype(np.uint8),
+                  pc_coord=rng.random((n // 3, 3)).astype(np.float32), pc_segment20=rng.integers(-1, 20, n // 3))
+    if with_segment:
+        arrays["segment20"] = rng.integers(-1, 20, (n, 1)).astype(np.int64)
+    for k, v in arrays.items():
+        np.save(os.path.join(path, k + ".npy"), v)
+    np.save(os.path.join(path, "unrelated.npy"), np.zeros(3))
+    return arrays
+
+
+@pytest.mark.parametrize("with_segment", [True, False])
+def test_packed_scene_equals_reference_get_data(tmp_path, with_segment):
+    """scene_io.pack_scene + load_scene returns exactly what the reference's get_data returns for the same folder
+    (oracle/scene_io.py restates scannetgs.py:59-150): same keys, dtypes, shapes, bytes.  Sections are 4 KiB aligned,
+    partial loads read only the requested attributes, a truncated file fails loudly."""
+    from oracle import scene_io as oio
+    from scenesplat_b200 import scene_io as sio
+    folder = str(tmp_path / "scene0000_00")
+    _write_scene_folder(folder, with_segment=with_segment)
+    want = oio.get_data(folder, is_train=False)
+    packed = str(tmp_path / "scene0000_00.sspk")
+    size = sio.pack_scene(folder, packed)
+    assert size == os.path.getsize(packed) and size % sio.ALIGN == 0
+    header, meta = sio.read_header(packed)
+    assert header % sio.ALIGN == 0 and all(e["offset"] % sio.ALIGN == 0 for e in meta["arrays"])
+    got = sio.load_scene(packed, pinned=False).numpy()
+    assert set(got) == set(want), (sorted(got), sorted(want))
+    for k in want:
+        assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+        np.testing.assert_array_equal(got[k], want[k])
+    assert got["scale"].max() <= 1.5 and got["lang_feat"].dtype == np.float16 and got["opacity"].shape[1] == 1
+    part = sio.load_scene(packed, keys=("coord", "quat"), pinned=False)
+    assert set(part.arrays) == {"coord", "quat"} and part.host.numel() < size // 4      # lang_feat was not read
+    np.testing.assert_array_equal(part.numpy()["quat"], want["quat"])
+    with pytest.raises(KeyError):
+        sio.load_scene(packed, keys=("nope",), pinned=False)
+    with open(packed, "r+b") as f:
+        f.truncate(size - 8192)
+    with pytest.raises(IOError):
+        sio.load_scene(packed, pinned=False)

@@ -321,3 +321,28 @@ def test_sphere_crop_golden(golden):
     # torch tensors in -> torch tensors (on the GPU) out; fewer points than point_max -> untouched
     d = dict(coord=dev(g["coord_in"][:100]))
     assert S.SphereCrop(point_max=1000)(d)["coord"].shape[0] == 100
+
+
+def test_packed_scene_one_copy_to_device(tmp_path):
+    """scene_io: the whole scene arrives on the GPU with ONE copy from ONE pinned buffer; every attribute is a view of
+    that device buffer and holds exactly the bytes the reference's get_data would produce (oracle/scene_io.py)."""
+    import os
+    from oracle import scene_io as oio
+    from scenesplat_b200 import scene_io as sio
+    from tests.test_cpu_host import _write_scene_folder
+    folder = str(tmp_path / "scene0001_00")
+    _write_scene_folder(folder, n=20000, seed=2)
+    want = oio.get_data(folder, is_train=True)
+    path = str(tmp_path / "scene0001_00.sspk")
+    sio.pack_scene(folder, path)
+    sc = sio.load_scene(path, keys=tuple(want))
+    assert sc.host.is_pinned()
+    dev_arrays = sc.to_device("cuda")
+    torch.cuda.synchronize()
+    base = {v.untyped_storage().data_ptr() for v in dev_arrays.values()}
+    assert len(base) == 1                                   # one device allocation behind all attributes
+    for k, v in want.items():
+        got = dev_arrays[k]
+        assert got.is_cuda and tuple(got.shape) == v.shape, k
+        np.testing.assert_array_equal(got.cpu().numpy(), v)
+    assert dev_arrays["lang_feat"].dtype == torch.float16   # stays fp16 until a kernel reads it
