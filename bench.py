@@ -45,7 +45,7 @@ N_RAW = 360000          # -> 299,277 voxels after GridSample(0.02) on the synthe
 CPU_SAMPLE_RAW = 120000  # bounded CPU sample: a ~100k-voxel sub-chunk of the same generator (10-30 s of CPU work)
 METRIC = "gaussians_per_s_ptv3_fwd"
 MUFU_PEAK_TEXP = 4.63                     # measured ex2 throughput of one B200, T/s (tools/micro/mufu.cu)
-ATTENTION_DRAM_BYTES_PER_LAUNCH = 290.4e6  # ncu dram read+write, mean of the 18 launches of a step (profiles/r1_launches_v3.md)
+ATTENTION_DRAM_BYTES_PER_LAUNCH = 290.1e6  # ncu dram read+write, mean of the 18 launches of a step (profiles/r1_launches_final.md: 5.22 GB over 18 launches)
 UNIT = "Gaussians/s"
 
 
