@@ -43,3 +43,15 @@ def confusion_update(gt, pred, num_classes, ignore_index, confusion, fn_ignore):
         else:
             confusion[g, p] += 1
     return confusion, fn_ignore
+
+
+def clustering_voting(pred, instance_labels, ignore_index):
+    """pointcept/utils/misc.py:98-125, restated line by line (numpy only)."""
+    updated = pred.copy()
+    for inst in np.unique(instance_labels):
+        if inst == ignore_index:
+            continue
+        mask = instance_labels == inst
+        classes, counts = np.unique(pred[mask], return_counts=True)
+        updated[mask] = classes[np.argmax(counts)]
+    return updated

@@ -11,7 +11,7 @@ from .ptv3 import (Block, Embedding, MLP, PointTransformerV3, SerializedAttentio
 from .lang import (AggregatedContrastiveLoss, ChunkPipeline, CosineSimilarity, Criteria, L2Loss,  # noqa: F401
                    LangPretrainer, zero_shot_accumulate, zero_shot_labels)
 from .transform import GridSample, SphereCrop  # noqa: F401
-from .voting import confusion_update, neighbor_voting  # noqa: F401
+from .voting import clustering_voting, confusion_update, neighbor_voting  # noqa: F401
 from .spconv_compat import SparseConvTensor, SubMConv3d  # noqa: F401
 from . import scene_io  # noqa: F401  (packed scene files: pack_scene / load_scene)
 from . import compat  # noqa: F401  (torch_scatter / flash_attn / spconv stand-ins: compat.install())

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["neighbor_voting", "confusion_update"]
+__all__ = ["neighbor_voting", "clustering_voting", "confusion_update"]
 
 
 def neighbor_voting(coords, pred, vote_k, ignore_label, num_classes, valid_mask=None, query_coords=None, cell=None):
@@ -75,3 +75,23 @@ def confusion_update(gt, pred, num_classes, ignore_index, confusion, fn_ignore):
     L.call("ss_confusion_update", L.ptr(gt), L.ptr(pred), gt.numel(), int(num_classes), int(ignore_index),
            L.ptr(confusion), L.ptr(fn_ignore), L.stream())
     return confusion, fn_ignore
+
+
+def clustering_voting(pred, instance_labels, ignore_index):
+    """pointcept/utils/misc.py:98-125 without the host loop over instances: every point of an instance (instance id !=
+    ignore_index) takes the instance's most frequent predicted label; ties go to the smallest label value (the
+    reference takes np.argmax over np.unique's ascending classes; the ignore label is a label value like any other).
+    One 2-D histogram (instances x label values) built with a device bincount, one argmax.  pred / instance_labels:
+    integer tensors [N] on the same device -> tensor like pred."""
+    if pred.shape != instance_labels.shape:
+        print("clustering_voting: prediction and instance arrays must have the same shape")
+        return pred
+    if pred.numel() == 0:
+        return pred.clone()
+    inst_vals, inst_idx = torch.unique(instance_labels, sorted=True, return_inverse=True)
+    cls_vals, cls_idx = torch.unique(pred, sorted=True, return_inverse=True)
+    ni, nc = inst_vals.numel(), cls_vals.numel()
+    hist = torch.bincount(inst_idx * nc + cls_idx, minlength=ni * nc).view(ni, nc)
+    major = cls_vals[torch.argmax(hist, dim=1)]          # first maximum = smallest label value
+    out = major[inst_idx]
+    return torch.where(instance_labels != ignore_index, out, pred)

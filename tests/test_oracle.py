@@ -186,3 +186,22 @@ def test_voting_oracle_small_cases():
     conf, fn = np.zeros((3, 3), np.int64), np.zeros(3, np.int64)
     ovote.confusion_update(np.array([0, 1, 2, 2]), np.array([0, -1, 2, 1]), 3, -1, conf, fn)
     assert conf.tolist() == [[1, 0, 0], [0, 0, 0], [0, 1, 1]] and fn.tolist() == [0, 1, 0]
+
+
+def test_clustering_voting_matches_the_restated_reference_loop():
+    """scenesplat_b200.clustering_voting (one histogram + argmax, torch) against the line-by-line restatement of
+    pointcept/utils/misc.py:98-125: ties -> smallest label value, the ignore label counts as a label, points of the
+    ignored instance keep their prediction.  Pure torch: runs on the CPU here and on CUDA tensors in production."""
+    import torch
+    from oracle import voting as ovote
+    from scenesplat_b200 import clustering_voting
+    rng = np.random.default_rng(5)
+    for n, n_inst, n_cls in ((1, 1, 3), (5000, 40, 20), (20000, 300, 200)):
+        pred = rng.integers(-1, n_cls, n).astype(np.int64)
+        inst = rng.integers(-1, n_inst, n).astype(np.int64)
+        inst[inst == 3] = 2                                   # a missing instance id
+        pred[inst == 5] = np.where(np.arange((inst == 5).sum()) % 2 == 0, 7 % n_cls, 2 % n_cls)  # an exact tie
+        want = ovote.clustering_voting(pred, inst, -1)
+        got = clustering_voting(torch.from_numpy(pred), torch.from_numpy(inst), -1)
+        np.testing.assert_array_equal(got.numpy(), want)
+    assert clustering_voting(torch.zeros(3, dtype=torch.long), torch.zeros(4, dtype=torch.long), -1).shape == (3,)
