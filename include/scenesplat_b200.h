@@ -180,6 +180,13 @@ int ss_patch_attention_backward(const void* qkv_bf16, const void* out_bf16, cons
                                 size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * MLP (point_transformer_v3m1_base.py:225-248): out = act(x W^T + b) on CTA pairs (tcgen05 cta_group::2), the
+ * activation fused into the TMEM epilogue.  x [n, cin] bf16, w [cout, cin] bf16 (nn.Linear layout), bias fp32 [cout] or
+ * NULL, act: 0 none, 1 exact GELU.  cin % 16 == 0, cout % 32 == 0. */
+int ss_linear_act_bf16(const void* x_bf16, const void* w_bf16, const float* bias, int64_t n, int cin, int cout, int act,
+                       void* out_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Row-wise fusions around the GEMMs of a Block (point_transformer_v3m1_base.py:318-338). */
 
 /* y = res + f(delta), f = LayerNorm(g0,b0) if g0 else identity; res_out = y (fp32, may alias res);

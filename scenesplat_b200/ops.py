@@ -317,6 +317,17 @@ def patch_attention_backward(qkv, out, dout, lse2, order_row, table, patch_size:
     return dqkv
 
 
+def linear_act(x_bf16, w_bf16, bias_f32=None, act=0):
+    """out = act(x W^T + b) on tcgen05 CTA pairs with the activation in the epilogue (act: 0 none, 1 exact GELU)."""
+    x_bf16, w_bf16 = x_bf16.contiguous(), w_bf16.contiguous()
+    n, cin = x_bf16.shape
+    cout = w_bf16.shape[0]
+    out = torch.empty((n, cout), dtype=_BF16, device=x_bf16.device)
+    L.call("ss_linear_act_bf16", L.ptr(x_bf16), L.ptr(w_bf16), L.ptr(bias_f32), n, cin, cout, int(act), L.ptr(out), L.stream(),
+           meta=dict(flops=2.0 * n * cin * cout, bytes=2.0 * (n * cin + n * cout + cin * cout)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------- row-wise fusions
 def add_layernorm(res, delta, ln0=None, ln1=None, eps=1e-5, want_res=True, norm_dtype=None, inplace=False):
     """y = res + LN0(delta) (LN0 optional); returns (y fp32 or None, LN1(y) / cast(y) or None)."""

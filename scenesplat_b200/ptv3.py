@@ -11,8 +11,10 @@ What changes underneath (eval / inference path):
   * SerializedPooling (ref :371-444): cluster ids / counts / pooled code, order, inverse of all rows come
     from run-length scans along the parent's orders (no unique, no sort), segment mean + BN + GELU fused.
   * SerializedUnpooling (ref :471-482): gather-add with both BN+GELU branches fused.
-Dense Linear layers stay library GEMMs (cuBLASLt through torch), in bf16 with fp32 accumulation.
-Training (autograd through these kernels) is not built yet -> forward raises under grad mode.
+  * MLP (ref :225-248): fc1 + bias + exact GELU is ONE tcgen05 kernel on CTA pairs (csrc/gemm2cta.cu); the xCPE Linear
+    is folded into the conv's per-tap weights.  The remaining dense Linear layers are library GEMMs (cuBLASLt
+    through torch), in bf16 with fp32 accumulation.
+Training (`model.train()` under autograd) takes scenesplat_b200/training.py.
 """
 from __future__ import annotations
 
@@ -242,11 +244,17 @@ class MLP(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        h = linear_bf16(self.fc1, x)
-        if isinstance(self.act, nn.GELU) and self.act.approximate == "none":
-            h = ops.affine_act(h, act=1)
+        fc1 = self.fc1
+        exact_gelu = isinstance(self.act, nn.GELU) and self.act.approximate == "none"
+        if exact_gelu and x.is_cuda and fc1.in_features % 16 == 0 and fc1.out_features % 32 == 0:
+            # fc1 + bias + GELU as ONE kernel on CTA pairs (csrc/gemm2cta.cu): the N x 4C hidden is written once
+            w, b = _cache.get(("lin_act", id(fc1)), [fc1.weight] + ([fc1.bias] if fc1.bias is not None else []),
+                              lambda: (fc1.weight.detach().to(BF16).contiguous(),
+                                       fc1.bias.detach().float().contiguous() if fc1.bias is not None else None))
+            h = ops.linear_act(x if x.dtype == BF16 else x.to(BF16), w, b, act=1)
         else:
-            h = self.act(h)
+            h = linear_bf16(fc1, x)
+            h = ops.affine_act(h, act=1) if exact_gelu else self.act(h)
         return linear_bf16(self.fc2, h)
 
 

@@ -208,3 +208,26 @@ def test_patch_attention_tensor_core(H, d, K):
     assert excess_simt <= 0, excess_simt
     rel = ((got.float().cpu() - want).norm() / want.norm()).item()
     assert rel < 1e-2, rel
+
+
+@pytest.mark.parametrize("n,cin,cout", [(1, 16, 32), (255, 48, 96), (257, 64, 256), (1000, 768, 3072), (5001, 3072, 768),
+                                        (70001, 512, 2048)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_linear_act_cta_pair(n, cin, cout, act):
+    """csrc/gemm2cta.cu (tcgen05 cta_group::2, fused bias + exact GELU) vs float64 on the same bf16 operands, incl. row /
+    column / K tails.  bf16 output of an fp32 accumulation: |err| <= 2^-8 |want| + 1e-3 * sqrt(cin) * 2^-8 (accumulation
+    order), and relative L2 < 4e-3."""
+    from scenesplat_b200 import ops
+    torch.manual_seed(n + cin)
+    x = torch.randn(n, cin).bfloat16()
+    w = (torch.randn(cout, cin) / cin ** 0.5).bfloat16()
+    b = torch.randn(cout)
+    got = ops.linear_act(x.cuda(), w.cuda(), b.cuda(), act).float().cpu()
+    want = x.double() @ w.double().t() + b.double()
+    if act:
+        want = F.gelu(want)
+    err = (got.double() - want).abs()
+    assert bool((err <= 2.0 ** -8 * want.abs() + 2e-3).all()), float(err.max())
+    assert float(err.norm() / want.norm()) < 4e-3
+    nob = ops.linear_act(x.cuda(), w.cuda(), None, 0).float().cpu()          # bias is optional
+    assert float((nob.double() - x.double() @ w.double().t()).abs().max()) <= 2.0 ** -7 * float(want.abs().max()) + 2e-3
