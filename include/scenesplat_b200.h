@@ -141,6 +141,12 @@ int ss_subm_conv_gemm(const void* in_bf16, const int32_t* pair_in, const void* w
 int ss_subm_conv_gemm256(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
                          int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream);
 
+/* Third generation of the same stage on CTA pairs (tcgen05 cta_group::2, csrc/conv_gemm3.cu): identical arguments and
+ * results; cout >= 256 (the 256-column slab is split between the two CTAs).  Double-buffered TMEM accumulators: the
+ * store of tile i overlaps the MMAs of tile i + 1. */
+int ss_subm_conv_gemm_pair(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
+                           int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream);
+
 /* out[p,:] = bias + sum_t prod[ypos[t][p], :]  (fp32 accumulate) -> bf16/fp32 */
 int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float* bias, int64_t n, int k3, int cout,
                         void* out, int out_is_bf16, void* stream);

@@ -35,6 +35,7 @@ SIGNATURES = {
     "ss_subm_conv_simt": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _i, _vp]),
     "ss_subm_conv_gemm": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "ss_subm_conv_gemm256": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
+    "ss_subm_conv_gemm_pair": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "ss_subm_conv_reduce": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp]),
     "ss_patch_table": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "ss_patch_attention_simt": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp]),

@@ -1,0 +1,258 @@
+// Submanifold convolution, stage 1 (gather-GEMM), third generation: CTA PAIRS (tcgen05 cta_group::2).
+//
+// Replaces (reference): spconv.SubMConv3d forward for the xCPE 3^3 convs
+// (point_transformer_v3m1_base.py:277-284; fp32 in the reference, bf16 x bf16 -> fp32 here).
+//
+//   prod[r, :] = X[pair_in[r], :] @ W_tap(r)^T        r < p_pad, taps contiguous and padded to 256 rows
+//
+// Same work items as conv_gemm2.cu (256 product rows x 256 output columns, slab-fastest), but a CTA pair shares one:
+// each CTA gathers its own 128 rows of A (cp.async, published by the copies themselves) and stages HALF of the 256
+// weight rows (TMA); the leader issues tcgen05.mma.cta_group::2 with M = 256.  One 128 x 256 fp32 accumulator per CTA
+// leaves the other 256 TMEM columns for a second buffer, so draining tile i (TMEM -> bf16 -> coalesced stores) runs
+// under the MMAs of tile i + 1 instead of stalling the tensor pipe (10 % of the time at C = 768, more at C = 256 / 512
+// where a tile has fewer K chunks).  Operand bytes staged per FLOP are unchanged (32 KB per 4.2 MFLOP per CTA).
+//
+// A and W live in SEPARATE rings: the gathers have ~3 us of latency under load and the kernel's rate is (gathered bytes in
+// flight) / latency, so A gets 7 slots of 16 KB and the TMA-fed W 4 (the pair halves W's footprint per CTA, which is what
+// makes room).  The leader's a_full barrier of a slot collects its own 128 gather threads
+// (cp.async.mbarrier.arrive.noinc) and one remote arrive from the peer's relay warp, which waits for the peer's own 128
+// gather arrivals; w_full counts the TMA bytes of BOTH weight halves.  Slot release and accumulator hand-over are
+// multicast commits.
+//
+// STATUS (end of round 1): bit-identical to conv_gemm2.cu but SLOWER (3.4 ms against 2.1 ms at the dec0 shape, 670 TFLOP/s);
+// it is not on the default path (ops.CONV_PAIR = 0).  Measured with the gathers switched off the kernel still runs at
+// 740 TFLOP/s while the dense pair kernel (gemm2cta.cu, A by TMA) reaches 1340: the loss is in the hand-over structure
+// (per-slot remote relay + two rings), not in the gathers, the slot count (5 -> 7 A slots: no change) or the number
+// of barrier arrivals (128 -> 32 per slot: no change).  Next: trace it (clock64 stamps per role) before tuning further.
+//
+// 15 warps per CTA: 0-7 epilogue (row quarter x column half), 8-11 A gather, 12 W producer (TMA, one lane),
+// 13 MMA issuer (leader) + TMEM allocator, 14 relay (peer).
+#include "pair_common.cuh"
+#include "../../include/scenesplat_b200.h"
+
+namespace ss {
+
+constexpr int kG3Threads = 480;
+constexpr int kG3BK = 64;
+constexpr int kG3SA = 7;  // A ring (gathered rows: ~3 us of latency under load, so as many bytes in flight as fit)
+constexpr int kG3SW = 4;  // W ring (TMA: a quarter of that latency)
+constexpr int kG3TileM = 256;
+constexpr int kG3BN = 256;
+
+struct Gemm3Smem {
+  static constexpr int kA = 128 * kG3BK * 2;  // this CTA's 128 gathered rows
+  static constexpr int kB = 128 * kG3BK * 2;  // this CTA's half of the weight rows
+  static constexpr int kOffW = kG3SA * kA;
+  static constexpr int kOffEpi = kOffW + kG3SW * kB;
+  static constexpr int kOffBar = kOffEpi + 8 * 2048;
+  static constexpr int kTotal = kOffBar + 512 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
+gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restrict__ pair_in,
+                        const __grid_constant__ CUtensorMap tmap_w, const int32_t* __restrict__ tile_tap, int cin, int cout,
+                        int n_slabs, int64_t n_items, __nv_bfloat16* __restrict__ prod) {
+  using S = Gemm3Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = (uint64_t*)(smem + S::kOffBar);  // [SA] leader: its 128 gathers + the peer's relay
+  uint64_t* a_done = a_full + kG3SA;                  // [SA] peer: its 128 gathers
+  uint64_t* a_empty = a_done + kG3SA;                 // [SA] one multicast commit
+  uint64_t* w_full = a_empty + kG3SA;                 // [SW] leader: expect_tx arrive, bytes of both halves
+  uint64_t* w_empty = w_full + kG3SW;                 // [SW] one multicast commit
+  uint64_t* acc_full = w_empty + kG3SW;               // [2]
+  uint64_t* acc_empty = acc_full + 2;                   // [2] leader's copy: 8 warps x 2 CTAs
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = pair::cta_rank();
+  const bool leader = rank == 0;
+  const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int nk = (cin + kG3BK - 1) / kG3BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kG3SA; ++s) {
+      tc::mbar_init(&a_full[s], 128 + 1);
+      tc::mbar_init(&a_done[s], 128);
+      tc::mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kG3SW; ++s) {
+      tc::mbar_init(&w_full[s], 1);
+      tc::mbar_init(&w_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&acc_full[b], 1);
+      tc::mbar_init(&acc_empty[b], 16);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 12 && lane == 0) tc::tma_prefetch_desc(&tmap_w);
+  if (warp == 13) pair::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  pair::cluster_sync();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8 && warp < 12) {
+    // ------------------------------------------------------------------ A gather: 128 threads, this CTA's 128 rows
+    const int tid = threadIdx.x - 256;      // 0..127
+    const int sub = tid >> 3, c = tid & 7;  // 8 lanes cover one 128-byte row segment
+    int64_t g = 0;
+    for (int64_t item = pair_id; item < n_items; item += n_pairs) {
+      const int64_t tile = item / n_slabs;
+      int32_t rows[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rows[i] = pair_in[tile * kG3TileM + rank * 128 + i * 16 + sub];
+      for (int kc = 0; kc < nk; ++kc, ++g) {
+        const int s = (int)(g % kG3SA);
+        // one poller per warp: 128 threads spinning on the barrier delay the (remote, multicast) arrival they wait for
+        if (lane == 0) tc::mbar_wait(&a_empty[s], (uint32_t)((g / kG3SA) & 1) ^ 1);
+        __syncwarp();
+        const uint32_t a_base = tc::smem_u32(smem + s * S::kA);
+        const int k0 = kc * kG3BK;
+        if (c < (min(kG3BK, cin - k0) >> 3)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 16 + sub;
+            tc::cp_async16(a_base + tc::sw128_offset(r, c), X + (size_t)rows[i] * cin + k0 + c * 8);
+          }
+        }
+        tc::cp_async_mbar_arrive_noinc(leader ? &a_full[s] : &a_done[s]);
+      }
+    }
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ W producer (TMA, one lane, both CTAs)
+    if (lane == 0) {
+      int64_t g = 0;
+      for (int64_t item = pair_id; item < n_items; item += n_pairs) {
+        const int64_t tile = item / n_slabs;
+        const int n0 = (int)(item - tile * n_slabs) * kG3BN;
+        const int tap = tile_tap[tile];
+        for (int kc = 0; kc < nk; ++kc, ++g) {
+          const int s = (int)(g % kG3SW);
+          tc::mbar_wait(&w_empty[s], (uint32_t)((g / kG3SW) & 1) ^ 1);
+          if (leader) tc::mbar_arrive_expect_tx(&w_full[s], 2 * S::kB);  // both weight halves
+          pair::tma_load_2d(tc::smem_u32(smem + S::kOffW + s * S::kB), &tmap_w, kc * kG3BK,
+                            tap * cout + n0 + (int)rank * 128, &w_full[s]);
+        }
+      }
+    }
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ relay (peer): "my 128 rows of the stage have landed"
+    if (!leader && lane == 0) {
+      int64_t g = 0;
+      for (int64_t item = pair_id; item < n_items; item += n_pairs)
+        for (int kc = 0; kc < nk; ++kc, ++g) {
+          const int s = (int)(g % kG3SA);
+          tc::mbar_wait(&a_done[s], (uint32_t)((g / kG3SA) & 1));
+          pair::mbar_arrive_cta(&a_full[s], 0);  // (release.cluster; no proxy fence: the leader's own gathers need none either)
+        }
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(kG3TileM, kG3BN);
+      const uint64_t d_base = tc::umma_desc_sw128(0);
+      const uint32_t s0 = tc::smem_u32(smem);
+      int64_t g = 0;
+      int it = 0;
+      for (int64_t item = pair_id; item < n_items; item += n_pairs, ++it) {
+        const int b = it & 1;
+        tc::mbar_wait(&acc_empty[b], (uint32_t)((it >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        for (int kc = 0; kc < nk; ++kc, ++g) {
+          const int sa = (int)(g % kG3SA), sw = (int)(g % kG3SW);
+          tc::mbar_wait(&w_full[sw], (uint32_t)((g / kG3SW) & 1));
+          tc::mbar_wait(&a_full[sa], (uint32_t)((g / kG3SA) & 1));
+          tc::tc_fence_after();
+          const uint32_t a0 = (s0 + sa * S::kA) >> 4;
+          const uint32_t b0 = (s0 + S::kOffW + sw * S::kB) >> 4;
+          const int ksteps = min(kG3BK, cin - kc * kG3BK) >> 4;
+          for (int k = 0; k < ksteps; ++k)
+            pair::umma_bf16_elect(tmem_base + b * kG3BN, d_base | (uint64_t)((a0 + 2 * k) & 0x3fff),
+                                  d_base | (uint64_t)((b0 + 2 * k) & 0x3fff), idesc, (kc | k) ? 1u : 0u);
+          pair::umma_commit_elect(&a_empty[sa]);
+          pair::umma_commit_elect(&w_empty[sw]);
+        }
+        pair::umma_commit_elect(&acc_full[b]);
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue warps 0..7: (row quarter, column half)
+    uint8_t* stg = smem + S::kOffEpi + warp * 2048;
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int it = 0;
+    for (int64_t item = pair_id; item < n_items; item += n_pairs, ++it) {
+      const int64_t tile = item / n_slabs;
+      const int n0 = (int)(item - tile * n_slabs) * kG3BN;
+      const int b = it & 1;
+      tc::mbar_wait(&acc_full[b], (uint32_t)((it >> 1) & 1));
+      tc::tc_fence_after();
+      __nv_bfloat16* obase = prod + ((size_t)tile * kG3TileM + rank * 128 + quarter * 32) * cout + n0 + half * 128;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        if (n0 + half * 128 + j * 32 >= cout) break;
+        uint32_t v[32];
+        tc::tmem_ld32(t_lane + b * kG3BN + half * 128 + j * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 o;
+          o.x = tc::pack_bf16(__uint_as_float(v[u * 8 + 0]), __uint_as_float(v[u * 8 + 1]));
+          o.y = tc::pack_bf16(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3]));
+          o.z = tc::pack_bf16(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5]));
+          o.w = tc::pack_bf16(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7]));
+          *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2), cc = lane & 3;
+          const uint4 o = *reinterpret_cast<const uint4*>(stg + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4));
+          *reinterpret_cast<uint4*>(obase + (size_t)r * cout + j * 32 + cc * 8) = o;
+        }
+        __syncwarp();
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) pair::mbar_arrive_cta(&acc_empty[b], 0);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  pair::cluster_sync();
+  if (warp == 13) {
+    tc::tc_fence_after();
+    pair::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace ss
+
+extern "C" int ss_subm_conv_gemm_pair(const void* in_bf16, const int32_t* pair_in, const void* w_bf16,
+                                      const int32_t* tile_tap, int64_t p_pad, int k3, int cin, int cout, void* prod_bf16,
+                                      void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (k3 < 1 || p_pad < 0 || p_pad % ss::kG3TileM != 0 || cin < 16 || cin % 16 != 0 || cout < 256 || cout % 32 != 0)
+    return SS_BAD_ARGS;
+  if (p_pad == 0) return SS_OK;
+  if (!in_bf16 || !pair_in || !w_bf16 || !tile_tap || !prod_bf16) return SS_BAD_ARGS;
+  if (((uintptr_t)in_bf16 | (uintptr_t)w_bf16 | (uintptr_t)prod_bf16) % 16 != 0) return SS_BAD_ARGS;
+  const int64_t tiles = p_pad / ss::kG3TileM;
+  // W viewed as one [k3 * cout, cin] K-major matrix, boxes of 128 rows (one CTA's half of a 256-column slab); a box that
+  // runs past a tap's last column reads the next tap's rows (or zeros past the end): those columns are never stored
+  CUtensorMap tmap;
+  int rc = ss::make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)k3 * cout, (uint64_t)cin, 128, ss::kG3BK);
+  if (rc) return rc;
+  auto kern = ss::gather_gemm_pair_kernel;
+  SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ss::Gemm3Smem::kTotal));
+  const int n_slabs = (cout + ss::kG3BN - 1) / ss::kG3BN;
+  const int64_t n_items = tiles * n_slabs;
+  const int pairs = (int)ss::imin64(n_items, ss::kNumSMs / 2);
+  kern<<<2 * pairs, ss::kG3Threads, ss::Gemm3Smem::kTotal, stream>>>((const __nv_bfloat16*)in_bf16, pair_in, tmap, tile_tap, cin,
+                                                                     cout, n_slabs, n_items, (__nv_bfloat16*)prod_bf16);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}

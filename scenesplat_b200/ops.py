@@ -199,6 +199,7 @@ def upload(values, dtype, device):
     return t.pin_memory().to(device, non_blocking=True)
 
 
+CONV_PAIR = int(os.environ.get("SS_CONV_PAIR", "0"))  # developer A/B switch: 1 = CTA-pair kernel (conv_gemm3.cu: correct, not yet faster)
 CONV_TILE = int(os.environ.get("SS_CONV_TILE", "256"))  # rows per gather-GEMM tile (128: first-generation kernel)
 
 
@@ -243,6 +244,8 @@ def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16
     p_pad = pairs["p_pad"]
     prod = torch.empty((max(p_pad, 1), cout), dtype=_BF16, device=x_bf16.device)
     fn = "ss_subm_conv_gemm256" if pairs.get("tile", 128) == 256 else "ss_subm_conv_gemm"
+    if fn == "ss_subm_conv_gemm256" and CONV_PAIR and cout >= 256:
+        fn = "ss_subm_conv_gemm_pair"  # CTA pairs, double-buffered accumulators (csrc/conv_gemm3.cu)
     L.call(fn, L.ptr(x_bf16.contiguous()), L.ptr(pairs["pair_in"]), L.ptr(w_bf16),
            L.ptr(pairs["tile_tap"]), p_pad, k3, cin, cout, L.ptr(prod), L.stream(),
            meta=dict(flops=2.0 * pairs["pairs"] * cin * cout, bytes=2.0 * pairs["pairs"] * (cin + cout)))
