@@ -332,7 +332,7 @@ def main():
             ms = float(t.item())
         return ms, prof, launches, clocks
 
-    hot = frozenset({"ss_patch_attention", "ss_subm_conv_gemm", "ss_subm_conv_gemm256"})  # the two candidates for "dominant own kernel"
+    hot = frozenset({"ss_patch_attention", "ss_subm_conv_gemm", "ss_subm_conv_gemm256", "ss_subm_conv_gemm_pair"})  # the two candidates for "dominant own kernel"
     ms, prof_hot, launches, clocks = timed(step_resident, args.steps, profile=hot)
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
     # full per-kernel table from a separate instrumented pass (events around ~350 calls/step perturb the step)

@@ -19,11 +19,11 @@
 // gather arrivals; w_full counts the TMA bytes of BOTH weight halves.  Slot release and accumulator hand-over are
 // multicast commits.
 //
-// STATUS (end of round 1): bit-identical to conv_gemm2.cu but SLOWER (3.4 ms against 2.1 ms at the dec0 shape, 670 TFLOP/s);
-// it is not on the default path (ops.CONV_PAIR = 0).  Measured with the gathers switched off the kernel still runs at
-// 740 TFLOP/s while the dense pair kernel (gemm2cta.cu, A by TMA) reaches 1340: the loss is in the hand-over structure
-// (per-slot remote relay + two rings), not in the gathers, the slot count (5 -> 7 A slots: no change) or the number
-// of barrier arrivals (128 -> 32 per slot: no change).  Next: trace it (clock64 stamps per role) before tuning further.
+// Measured at the dec0 shape (1.94 M pairs, C = 768): 1.91 ms = 1202 TFLOP/s useful against 2.06 ms (1115) for
+// conv_gemm2.cu, at C = 512: 0.219 against 0.252 ms; bit-identical products.  What made the difference: the peer's relay
+// must not be one thread issuing one release-arrive per slot in sequence (a remote arrive has microseconds of latency:
+// 670 TFLOP/s, and 740 even with the gathers switched off); with one relay lane per slot and relaxed arrives the
+// hand-overs overlap.
 //
 // 15 warps per CTA: 0-7 epilogue (row quarter x column half), 8-11 A gather, 12 W producer (TMA, one lane),
 // 13 MMA issuer (leader) + TMEM allocator, 14 relay (peer).
@@ -140,14 +140,15 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
     }
   } else if (warp == 14) {
     // ------------------------------------------------------------------ relay (peer): "my 128 rows of the stage have landed"
-    if (!leader && lane == 0) {
-      int64_t g = 0;
-      for (int64_t item = pair_id; item < n_items; item += n_pairs)
-        for (int kc = 0; kc < nk; ++kc, ++g) {
-          const int s = (int)(g % kG3SA);
-          tc::mbar_wait(&a_done[s], (uint32_t)((g / kG3SA) & 1));
-          pair::mbar_arrive_cta(&a_full[s], 0);  // (release.cluster; no proxy fence: the leader's own gathers need none either)
-        }
+    // one lane per A slot: a remote arrive has microseconds of latency, so the slots' hand-overs must overlap
+    if (!leader && lane < kG3SA) {
+      int64_t my_items = 0;
+      for (int64_t item = pair_id; item < n_items; item += n_pairs) ++my_items;
+      const int64_t total = my_items * nk;
+      for (int64_t g = lane; g < total; g += kG3SA) {
+        tc::mbar_wait(&a_done[lane], (uint32_t)((g / kG3SA) & 1));
+        pair::mbar_arrive_cta_relaxed(&a_full[lane], 0);
+      }
     }
   } else if (warp == 13) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)

@@ -63,6 +63,16 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t target) 
       "r"(target)
       : "memory");
 }
+// same, without the release fence (a flag hand-over: the data it announces was written by asynchronous copies whose
+// completion the caller has already observed through a local mbarrier)
+__device__ __forceinline__ void mbar_arrive_cta_relaxed(uint64_t* bar, uint32_t target) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(tc::smem_u32(bar)),
+      "r"(target)
+      : "memory");
+}
 }  // namespace pair
 
 }  // namespace ss

@@ -199,7 +199,7 @@ def upload(values, dtype, device):
     return t.pin_memory().to(device, non_blocking=True)
 
 
-CONV_PAIR = int(os.environ.get("SS_CONV_PAIR", "0"))  # developer A/B switch: 1 = CTA-pair kernel (conv_gemm3.cu: correct, not yet faster)
+CONV_PAIR = int(os.environ.get("SS_CONV_PAIR", "1"))  # developer A/B switch: 0 = single-CTA 256-row kernel for every width
 CONV_TILE = int(os.environ.get("SS_CONV_TILE", "256"))  # rows per gather-GEMM tile (128: first-generation kernel)
 
 

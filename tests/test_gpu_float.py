@@ -80,13 +80,14 @@ def test_subm_conv_tensor_core(c, tile):
     rel = ((got.cpu() - want).norm() / want.norm()).item()
     assert rel < 5e-3, rel
     if tile == 256 and c >= 256:
-        # the CTA-pair generation (csrc/conv_gemm3.cu, opt-in) computes the same products in the same order: bit-identical
-        ops.CONV_PAIR = 1
+        # the CTA-pair generation (csrc/conv_gemm3.cu, the default for C >= 256) and the single-CTA kernel compute the
+        # same products in the same order: bit-identical
+        saved, ops.CONV_PAIR = ops.CONV_PAIR, 1 - ops.CONV_PAIR
         try:
-            got_pair = ops.subm_conv_gemm(x.cuda(), pairs, wk, b.cuda(), n, out_dtype=torch.float32)
+            got_other = ops.subm_conv_gemm(x.cuda(), pairs, wk, b.cuda(), n, out_dtype=torch.float32)
         finally:
-            ops.CONV_PAIR = 0
-        assert torch.equal(got_pair, got)
+            ops.CONV_PAIR = saved
+        assert torch.equal(got_other, got)
 
 
 @pytest.mark.parametrize("H,d,K,dtype", [(2, 16, 64, torch.float32), (4, 16, 1024, torch.bfloat16),
