@@ -33,7 +33,7 @@
 #define SS_ATT_WIDE 1
 #endif
 #ifndef SS_ATT_POLY
-#define SS_ATT_POLY 3
+#define SS_ATT_POLY 2
 #endif
 #ifndef SS_ATT_PP
 #define SS_ATT_PP 1
@@ -884,7 +884,8 @@ static int launch_attention_var(const void* qkv, const int64_t* order_row, const
 
 // Variant selection is a COMPILE-time choice (no environment lookups, no global state in the library):
 //   SS_ATT_WIDE  1 = 16-softmax-warp kernel (default), 0 = 8-softmax-warp kernel
-//   SS_ATT_POLY  exponentials per 8 evaluated on the FMA pipe (default 3)
+//   SS_ATT_POLY  exponentials per 8 evaluated on the FMA pipe (default 2; measured 2..5 at the end of round 1:
+//                2 and 3 tie at d = 48, 2 is 3 % faster at d = 16 / 32)
 //   SS_ATT_PP    group ping-pong of the wide kernel (default 1)
 // tools/micro/att_bench.cu includes this file and can be built with other values for A/B runs.
 template <int D>
