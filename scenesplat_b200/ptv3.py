@@ -116,7 +116,7 @@ def cpe_folded(conv, lin: nn.Linear):
 
 def ln_params(ln: nn.LayerNorm):
     return _cache.get(("ln", id(ln)), [ln.weight, ln.bias],
-                      lambda: (ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous()))
+                      lambda: (ln.weight.detach().float().clone(), ln.bias.detach().float().clone()))  # own, aligned storage
 
 
 def bn_fold(bn: nn.BatchNorm1d):
@@ -250,7 +250,7 @@ class MLP(nn.Module):
             # fc1 + bias + GELU as ONE kernel on CTA pairs (csrc/gemm2cta.cu): the N x 4C hidden is written once
             w, b = _cache.get(("lin_act", id(fc1)), [fc1.weight] + ([fc1.bias] if fc1.bias is not None else []),
                               lambda: (fc1.weight.detach().to(BF16).contiguous(),
-                                       fc1.bias.detach().float().contiguous() if fc1.bias is not None else None))
+                                       fc1.bias.detach().float().clone() if fc1.bias is not None else None))
             h = ops.linear_act(x if x.dtype == BF16 else x.to(BF16), w, b, act=1)
         else:
             h = linear_bf16(fc1, x)
