@@ -13,7 +13,10 @@ JSON keys (one line, rank 0): see the harness contract.  `value` = device-reside
 `e2e` = the same forward driven through the public API (LangPretrainer + zero-shot head) from PINNED
 HOST buffers with the H2D copy of the inputs and the D2H read of the labels inside the timed region,
 `roofline` = the dominant own kernel timed with CUDA events inside the timed region,
-`cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
+`cpu_baseline` = the CPU oracle port timed on this box's host cores on the SAME chunk (one forward),
+`parity` = the benchmarked model's output on the benchmarked chunk against that oracle forward.
+Extra keys measured in the same run (BASELINE.json configs 1, 3, 4, 5 and the same-box library bars):
+`serialize_pool_hbm`, `train_step`, `zero_shot_scene`, `sweep`, `library_bars` (tools/workloads.py).
 """
 from __future__ import annotations
 
@@ -42,7 +45,7 @@ LANG_BACKBONE = dict(
     enable_flash=True, upcast_attention=False, upcast_softmax=False, cls_mode=False,
 )
 N_RAW = 360000          # -> 299,277 voxels after GridSample(0.02) on the synthetic room (seed 0)
-CPU_SAMPLE_RAW = 120000  # bounded CPU sample: a ~100k-voxel sub-chunk of the same generator (10-30 s of CPU work)
+PARITY_SEED = 11        # CPU-RNG seed of the parity forward (order shuffles: serialization + three pooling levels)
 METRIC = "gaussians_per_s_ptv3_fwd"
 MUFU_PEAK_TEXP = 4.63                     # measured ex2 throughput of one B200, T/s (tools/micro/mufu.cu)
 ATTENTION_DRAM_BYTES_PER_LAUNCH = 290.1e6  # ncu dram read+write, mean of the 18 launches of a step (profiles/r1_launches_final.md: 5.22 GB over 18 launches)
@@ -153,46 +156,84 @@ def voxelize_on_gpu(d, dev):
     return dev_in, host_in, n
 
 
-def cpu_oracle_throughput(threads=None):
-    """The CPU restatement of the reference forward (oracle/ptv3.py) on a bounded sample; Gaussians/s."""
-    from oracle import gridsample as ogs
+def oracle_forward(coord, grid_coord, feat, perms, threads=None):
+    """One forward of the CPU restatement of the reference model (oracle/ptv3.py, fp32, torch CPU threads) with the
+    bench model's weights.  -> (features [n, 768] fp32, seconds, threads used)."""
     from oracle import ptv3 as optv3
-    from scenesplat_b200 import synthetic
     ncpu = os.cpu_count() or 1
     torch.set_num_threads(threads or ncpu)
-    d = synthetic.chunk(CPU_SAMPLE_RAW, L=3.5, H=3.0, seed=0)
-    res = ogs.grid_sample_train(d["coord"], 0.02)
-    idx = res["idx_unique"]
-    feat = synthetic.feat_from({k: v[idx] for k, v in d.items()})
-    n = idx.shape[0]
     cfg = {k: v for k, v in LANG_BACKBONE.items() if k != "type"}
     model = build_model()
     sd = {k[len("backbone."):]: v for k, v in model.state_dict().items()}
-    perms = [np.arange(4)] * 4
+    n = coord.shape[0]
     t0 = time.perf_counter()
-    optv3.ptv3_forward(sd, cfg, d["coord"][idx], res["grid_coord"], feat, np.array([n]), perms=perms)
+    out = optv3.ptv3_forward(sd, cfg, np.asarray(coord), np.asarray(grid_coord), np.asarray(feat), np.array([n]),
+                             perms=[np.asarray(p) for p in perms])
     dt = time.perf_counter() - t0
-    return n / dt, n, dt, torch.get_num_threads()
+    return out, dt, torch.get_num_threads()
+
+
+def parity_perms(seed=PARITY_SEED):
+    """The four row permutations `torch.randperm(4)` yields after `torch.manual_seed(seed)`: the GPU forward draws
+    them from the CPU generator in the reference's order; the oracle takes them as a list."""
+    torch.manual_seed(seed)
+    return [torch.randperm(4).numpy() for _ in range(4)]
+
+
+def parity_metrics(got, want, text):
+    """got / want: backbone outputs [n, 768] (before the L2 normalisation of LangPretrainer)."""
+    got, want = got.float().cpu(), want.float().cpu()
+    rel = ((got - want).norm() / want.norm()).item()
+    cos = torch.nn.functional.cosine_similarity(got, want, dim=1)
+    t = text.float().cpu()
+    lg = torch.nn.functional.normalize(got, dim=1) @ t.t()
+    lw = torch.nn.functional.normalize(want, dim=1) @ t.t()
+    agree = (lg.argmax(1) == lw.argmax(1)).float().mean().item()
+    return dict(rel_l2=rel, cos_mean=cos.mean().item(), cos_min=cos.min().item(), label_agreement_k200=agree,
+                voxels=int(got.shape[0]), depths="enc (2,2,2,6) / dec (2,2,2) = the benchmarked model",
+                tolerance="rel_l2 < 3e-2, cos_mean > 0.999 (bf16 operands, fp32 accumulate, vs the fp32 oracle)",
+                ok=bool(rel < 3e-2 and cos.mean().item() > 0.999))
+
+
+def cpu_chunk(n_raw=N_RAW):
+    """The benchmark chunk voxelised on the CPU (reference arm: no GPU involved)."""
+    from oracle import gridsample as ogs
+    from scenesplat_b200 import synthetic
+    d = synthetic.chunk(n_raw, seed=0)
+    np.random.seed(0)
+    res = ogs.grid_sample_train(d["coord"], 0.02)
+    idx = res["idx_unique"]
+    feat = synthetic.feat_from({k: v[idx] for k, v in d.items()})
+    return d["coord"][idx], res["grid_coord"], feat
 
 
 def run_reference_arm(args):
+    """The CPU arm: the oracle port of the reference forward (the reference is Python over spconv / flash_attn /
+    torch_scatter CUDA builds that are absent offline) on the box's host cores, on the SAME
+    chunk as the GPU arm (one full forward per step; steps bounded so the run ends within minutes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    n = dt = cores = None
-    for i in range(max(1, min(args.steps, 3)) + min(args.warmup, 1)):
-        v, n, dt, cores = cpu_oracle_throughput()
-        if i >= min(args.warmup, 1):
-            vals.append(v)
+    coord, gc, feat = cpu_chunk(args.n_raw)
+    n = coord.shape[0]
+    perms = [np.arange(4)] * 4
+    steps, warm = max(1, min(args.steps, 2)), min(args.warmup, 1)
+    vals, dts, cores = [], [], None
+    for i in range(steps + warm):
+        _, dt, cores = oracle_forward(coord, gc, feat, perms)
+        if i >= warm:
+            vals.append(n / dt)
+            dts.append(dt)
     value = float(np.mean(vals))
-    sample = f"oracle/ptv3.py full-size lang PT-v3m1 forward (fp32, torch CPU) on a {n}-voxel synthetic sub-chunk"
-    line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=len(vals),
-                warmup=min(args.warmup, 1), ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="fp32", data="synthetic",
-                config=dict(workload="SceneSplat lang-pretrain PTv3 encoder forward, synthetic ScanNet-sized chunk "
-                                     "(CPU port timed on a bounded sub-chunk of the same generator)",
-                            voxels_per_step=n, patch_size=1024),
+    sample = (f"oracle/ptv3.py: the full lang PT-v3m1 forward (fp32, torch CPU) on the benchmark chunk itself "
+              f"({n} voxels), {steps} timed forward(s) of {np.mean(dts):.1f} s")
+    line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=steps, warmup=warm,
+                ms_per_step=1e3 * float(np.mean(dts)), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="fp32", data="synthetic",
+                config=dict(workload="SceneSplat lang-pretrain PTv3 encoder forward (PT-v3m1 lang config, 91.7M params, "
+                                     "random init, eval), one synthetic ScanNet-sized chunk, patch 1024",
+                            voxels_per_chunk=n, raw_gaussians_per_chunk=args.n_raw, grid_size=0.02,
+                            note="CPU arm: oracle port, same chunk as the GPU arm; steps bounded to 2 x ~30 s"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -204,7 +245,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle forward (cpu_baseline, parity)")
+    ap.add_argument("--no-extras", action="store_true", help="skip train_step / zero_shot_scene / sweep / library bars")
     ap.add_argument("--n-raw", type=int, default=N_RAW)
     ap.add_argument("--no-pipeline", action="store_true", help="one chunk at a time (index phase not overlapped)")
     args = ap.parse_args()
@@ -221,15 +263,29 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback in the product path)")
+    # N ranks share one host: give every rank its own slice of the cores (8 ranks contending for the same cores was
+    # one suspect of the 4 % scaling loss of round 1) and keep the BLAS / OpenMP pools small
+    ncpu = os.cpu_count() or 1
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        per = max(1, ncpu // world)
+        try:
+            os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
+        except OSError:
+            pass
+        torch.set_num_threads(max(1, min(4, per)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if rank == 0:
         ClockSampler.init_nvml()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # >= 10 untimed steps: the first ~10 forwards of a process still grow torch's caching allocator (cudaMalloc of
-    # multi-GB segments = 70-250 ms stalls) and cuBLASLt's heuristic cache; steady state is what is measured
-    warm = max(args.warmup, 10)
+    warm = max(args.warmup, 3)  # the harness asks for >= 3 untimed steps; --warmup is honoured as given above that
+
+    # Allocator pre-warm (setup, not part of any step): reserve the step's working set once so the timed region never
+    # waits for the driver to map memory.  The block goes back to torch's caching allocator and is carved up by the
+    # forwards; nothing computed is cached.
+    pre = torch.empty(24 << 30, dtype=torch.uint8, device=dev)
+    del pre
 
     model = build_model().to(dev)
     text = torch.nn.functional.normalize(torch.randn(200, 768, generator=torch.Generator().manual_seed(1)), dim=1).to(dev)
@@ -275,26 +331,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    settle_steps = []
+    def gather_ranks(x):
+        """-> list of one float per rank."""
+        if world == 1:
+            return [float(x)]
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[rank] = float(x)
+        dist.all_reduce(t)
+        return t.tolist()
 
-    def timed(fn, steps, profile=None, sample=True):
+    def timed(fn, steps, profile=None, sample=True, n_warm=None):
         """profile: None = no per-call events; a set = events around those C-ABI calls only; "all" = every call."""
-        for _ in range(warm):
+        for _ in range(warm if n_warm is None else n_warm):
             fn()
-        # settle: the first second or so of sustained load on a fresh box shows isolated 1.5-4x slow steps (clock /
-        # power-limiter transients); keep warming up (untimed) until 8 consecutive steps agree within 6 %
-        hist, extra = [], 0
-        while extra < 160:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            b.synchronize()
-            hist.append(a.elapsed_time(b))
-            extra += 1
-            if len(hist) >= 8 and max(hist[-8:]) < 1.06 * min(hist[-8:]):
-                break
-        settle_steps.append(extra)
         gc.collect()
         gc.freeze()  # keep cyclic-GC pauses (tens of ms with ~10^5 live objects) out of the timed region
         barrier()
@@ -317,24 +366,24 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        if rank == 0 and os.environ.get("BENCH_VERBOSE"):
-            prev, per = e0, []
-            for ev in marks:
-                per.append(round(prev.elapsed_time(ev), 1))
-                prev = ev
-            print("per-step device ms", per, "host enqueue ms", [round(c, 1) for c in cpu_ms], file=sys.stderr, flush=True)
+        prev, per = e0, []
+        for ev in marks:
+            per.append(prev.elapsed_time(ev))
+            prev = ev
         prof, L.PROFILE, L.PROFILE_ONLY = L.PROFILE, None, None
         launches = L.launch_count() - l0
         clocks = sampler.stop() if sampler else None
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, prof, launches, clocks
+        rank_ms = gather_ranks(ms / steps)
+        rank_host = gather_ranks(float(np.median(cpu_ms)))
+        stats = dict(p50=float(np.percentile(per, 50)), p95=float(np.percentile(per, 95)), min=float(min(per)),
+                     max=float(max(per)), host_enqueue_ms_p50=float(np.median(cpu_ms)),
+                     per_rank_ms_per_step=[round(v, 3) for v in rank_ms],
+                     per_rank_host_enqueue_ms=[round(v, 3) for v in rank_host])
+        return max(rank_ms) * steps, prof, launches, clocks, stats
 
-    hot = frozenset({"ss_patch_attention", "ss_subm_conv_gemm", "ss_subm_conv_gemm256", "ss_subm_conv_gemm_pair"})  # the two candidates for "dominant own kernel"
-    ms, prof_hot, launches, clocks = timed(step_resident, args.steps, profile=hot)
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+    hot = frozenset({"ss_patch_attention", "ss_subm_conv_gemm256", "ss_subm_conv_gemm_pair"})  # the two candidates for "dominant own kernel"
+    ms, prof_hot, launches, clocks, step_stats = timed(step_resident, args.steps, profile=hot)
+    ms_e2e, _, _, _, e2e_stats = timed(step_e2e, args.steps)
     # full per-kernel table from a separate instrumented pass (events around ~350 calls/step perturb the step)
     # (one chunk at a time: per-call events of two overlapping streams would charge the small index kernels with the
     # time they spend waiting for SMs behind the feature phase of the previous chunk)
@@ -343,13 +392,9 @@ def main():
         with torch.no_grad():
             return model(dict(dev_in))["point_feat"]["feat"]
 
-    _, prof, _, _ = timed(step_sequential, max(2, args.steps // 2), profile="all", sample=False)
     prof_steps = max(2, args.steps // 2)
-    total_vox = n_vox
-    if world > 1:
-        t = torch.tensor([n_vox], device=dev, dtype=torch.float64)
-        dist.all_reduce(t)
-        total_vox = float(t.item())
+    _, prof, _, _, _ = timed(step_sequential, prof_steps, profile="all", sample=False, n_warm=2)
+    total_vox = sum(gather_ranks(n_vox))
     value = total_vox * args.steps / (ms * 1e-3)
     e2e_value = total_vox * args.steps / (ms_e2e * 1e-3)
 
@@ -371,26 +416,24 @@ def main():
     roofline = None
     if top[0] is not None:
         name, r = top
-        if r["flops"] > 0:
-            ach = r["flops"] / (r["ms"] * 1e-3) / 1e12
-            roofline = dict(kernel=name, bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s",
-                            frac=ach / pk["tf_sust"], traffic=None, peak_source=pk["src"] + " (sustained bf16)",
-                            share_of_step=r["ms"] / ms, calls_per_step=r["calls"] / args.steps)
-            if name == "ss_patch_attention":
-                # measured once per kernel version with ncu (profiles/r1_attention_ncu.md): DRAM bytes per launch,
-                # averaged over the 18 launches of a step like `achieved`
-                roofline["traffic"] = ATTENTION_DRAM_BYTES_PER_LAUNCH
-                # the binding pipe at head dims 16..48 is MUFU (one exponential per score), not the tensor pipe:
-                # 4 d FLOPs per exponential caps the FLOP rate at 4 d x the MUFU rate (d = 48: 0.89 PFLOP/s)
-                exp_rate = r["exps"] / (r["ms"] * 1e-3)
-                roofline["binding_pipe"] = dict(pipe="MUFU.EX2", achieved=exp_rate / 1e12, peak=MUFU_PEAK_TEXP, unit="Texp/s",
-                                                frac=exp_rate / 1e12 / MUFU_PEAK_TEXP,
-                                                peak_source="measured, tools/micro/mufu.cu (16 / clk / SM at 1.955 GHz)")
-        else:
-            ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
-            roofline = dict(kernel=name, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
-                            traffic=None, peak_source=pk["src"], share_of_step=r["ms"] / ms,
-                            calls_per_step=r["calls"] / args.steps)
+        ach = r["flops"] / (r["ms"] * 1e-3) / 1e12
+        roofline = dict(kernel=name, bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s",
+                        frac=ach / pk["tf_sust"], traffic=None, peak_source=pk["src"] + " (sustained bf16)",
+                        share_of_step=r["ms"] / ms, calls_per_step=r["calls"] / args.steps,
+                        ms_per_step=r["ms"] / args.steps)
+        if name == "ss_patch_attention":
+            # measured once per kernel version with ncu (profiles/): DRAM bytes per launch, averaged over the 18
+            # launches of a step like `achieved`
+            roofline["traffic"] = ATTENTION_DRAM_BYTES_PER_LAUNCH
+            # the binding pipe at head dims 16..48 is MUFU (one exponential per score), not the tensor pipe:
+            # 4 d FLOPs per exponential caps the FLOP rate at 4 d x the MUFU rate (d = 48: 0.89 PFLOP/s)
+            exp_rate = r["exps"] / (r["ms"] * 1e-3)
+            roofline["binding_pipe"] = dict(pipe="MUFU.EX2", achieved=exp_rate / 1e12, peak=MUFU_PEAK_TEXP, unit="Texp/s",
+                                            frac=exp_rate / 1e12 / MUFU_PEAK_TEXP,
+                                            peak_source="measured, tools/micro/mufu.cu (16 / clk / SM at 1.955 GHz)")
+        roofline["other_hot_kernels"] = {
+            k: dict(ms_per_step=v["ms"] / args.steps, tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12,
+                    frac=v["flops"] / (v["ms"] * 1e-3) / 1e12 / pk["tf_sust"]) for k, v in hot_table.items() if k != name}
     own_ms = sum(r["ms"] for r in own.values()) / prof_steps
     # the second half of BASELINE.json's metric: serialize + pool achieved HBM GB/s (algorithmic bytes of SURVEY 8d:
     # 128 B / Gaussian for the 4-order serialization, N (28 + C e) + M (148 + 4 C) for a pooling level)
@@ -400,16 +443,66 @@ def main():
         sp_bytes, sp_ms = sum(r["bytes"] for r in sp), sum(r["ms"] for r in sp)
         serialize_pool = dict(gbs=sp_bytes / (sp_ms * 1e-3) / 1e9, frac_of_hbm=sp_bytes / (sp_ms * 1e-3) / 1e9 / pk["hbm"],
                               ms_per_step=sp_ms / prof_steps, bytes_per_step=sp_bytes / prof_steps,
-                              note="small launches (serialization 38 MB, three pooling levels): latency-bound at 300 k Gaussians")
+                              by_kernel={k: dict(ms_per_step=table[k]["ms"] / prof_steps,
+                                                 gbs=table[k]["bytes"] / (table[k]["ms"] * 1e-3) / 1e9)
+                                         for k in ("ss_serialize", "ss_pool_index", "ss_segment_reduce") if k in table},
+                              note="device time of the serialization + the three pooling levels of the benchmark chunk")
+
+    # ---- parity of the benchmarked configuration + the CPU baseline (one oracle forward on the same chunk)
+    cpu = parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        perms = parity_perms()
+        torch.manual_seed(PARITY_SEED)
+        with torch.no_grad():
+            got = model.backbone(dict(dev_in)).feat.float().cpu()
+        want, dt, cores = oracle_forward(host_in["coord"].numpy(), host_in["grid_coord"].numpy(),
+                                         host_in["feat"].numpy(), perms)
+        parity = parity_metrics(got, want, text)
+        cpu = dict(value=n_vox / dt, unit=UNIT, cores=cores, kind="port",
+                   sample=f"oracle/ptv3.py: one full lang PT-v3m1 forward (fp32) on the benchmark chunk itself "
+                          f"({n_vox} voxels), {dt:.1f} s")
+        del got, want
+
+    # ---- secondary workloads (BASELINE.json configs 1, 3, 4, 5) and the same-box library bars
+    extras = {}
+    if not args.no_extras:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import workloads as W
+
+        def guarded(name, fn):
+            try:
+                t0 = time.perf_counter()
+                extras[name] = fn()
+                if isinstance(extras[name], dict):
+                    extras[name]["bench_wall_s"] = round(time.perf_counter() - t0, 1)
+            except Exception as e:  # a failing extra must not take the headline line with it
+                extras[name] = dict(error=repr(e)[:300])
+            torch.cuda.synchronize()
+
+        if rank == 0 and world == 1:
+            def index_config1():
+                g = W.gpu_index_config1(dev)
+                g["torch_gpu"] = W.torch_index_config1(dev)
+                if not args.no_cpu_baseline:
+                    g["cpu_baseline"] = W.cpu_index_config1()
+                    g["speedup_vs_cpu"] = g["cpu_baseline"]["total_ms"] / g["total_ms"]
+                g["frac_of_hbm"] = g["gbs"] / pk["hbm"]
+                return g
+            guarded("index_config1", index_config1)
+            guarded("library_bars", lambda: dict(attention=W.attention_library_bar(dev)))
+        guarded("zero_shot_scene", lambda: W.zero_shot_scene(dev, model, text))
+        guarded("sweep", lambda: dict(rows=W.sweep(dev, rank, world, model, text, cpu_rate=cpu["value"] if cpu else None),
+                                      policy="lpt", chunk_rule="6 m x 6 m windows, 3 m stride, >= 10000 points"))
+        gen_resident = gen_e2e = None  # drop the pipelines' cached points before the training workload
+        gc.unfreeze()
+        gc.collect()
+        torch.cuda.empty_cache()
+        guarded("train_step", lambda: W.train_step(dev, rank, world, LANG_BACKBONE))
 
     if rank == 0:
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            v, n, dt, cores = cpu_oracle_throughput()
-            cpu = dict(value=v, unit=UNIT, cores=cores, kind="port",
-                       sample=f"oracle/ptv3.py full-size lang PT-v3m1 forward (fp32) on a {n}-voxel synthetic sub-chunk, "
-                              f"{dt:.1f} s")
         h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+        if serialize_pool is not None and "index_config1" in extras:
+            serialize_pool["config1"] = extras.pop("index_config1")
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm,
             ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
@@ -422,14 +515,15 @@ def main():
                                   "index phase (+ H2D) of chunk i+1 on a side stream under the feature phase of chunk i"),
                         l2="256 MiB flush buffer written before every step; activations (GBs) exceed L2 anyway"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=n_vox * 12,
-                     ms_per_step=ms_e2e / args.steps,
+                     ms_per_step=ms_e2e / args.steps, step_ms=e2e_stats,
                      api="ChunkPipeline(LangPretrainer(eval)) + zero_shot_labels(K=200) from pinned host inputs"),
-            gpu_launches=launches, own_kernel_ms_per_step=own_ms, extra_settle_warmup_steps=settle_steps,
+            gpu_launches=launches, own_kernel_ms_per_step=own_ms, step_ms=step_stats,
             kernels={k: dict(ms_per_step=round(v["ms"] / prof_steps, 4), calls_per_step=v["calls"] / prof_steps)
                      for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])},
             kernels_note="per-call CUDA-event times from a separate instrumented, non-pipelined pass; the roofline kernel "
                          "is timed inside the timed region itself",
-            roofline=roofline, serialize_pool_hbm=serialize_pool, cpu_baseline=cpu, clocks=clocks,
+            roofline=roofline, parity=parity, serialize_pool_hbm=serialize_pool, cpu_baseline=cpu, clocks=clocks,
+            **extras,
         )
         print(json.dumps(line), flush=True)
     if world > 1:

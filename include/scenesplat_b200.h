@@ -130,18 +130,14 @@ size_t ss_stem_conv_wgrad_workspace_bytes(int k3, int cin);
 int ss_stem_conv_wgrad(const float* in, const float* dy, const int32_t* nbr, int64_t n, int k3, int cin, int cout,
                        float* dw, void* workspace, size_t workspace_bytes, void* stream);
 
-/* tcgen05 gather-GEMM: prod[r, :] = in[pair_in[r], :] @ w[tap(r)]^T for r < p_pad (bf16 in, fp32
- * accumulate in TMEM, bf16 out).  w is [k^3, cout, cin] bf16 (K-major), tile_tap_host [p_pad/128]
- * int32 gives the tap of every 128-row tile.  cin, cout multiples of 16 (cout <= 768...). */
-int ss_subm_conv_gemm(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
-                      int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream);
-
-/* Same product, second-generation kernel: persistent CTAs, 256-row tiles (two M=128 accumulators share every
- * W stage).  tile_tap [p_pad/256] gives the tap of every 256-row tile; every tap segment is padded to 256 rows. */
+/* tcgen05 gather-GEMM, first stage of the xCPE conv: prod[r, :] = in[pair_in[r], :] @ w[tap(r)]^T for r < p_pad
+ * (bf16 in, fp32 accumulate in TMEM, bf16 out).  w is [k^3, cout, cin] bf16 (K-major); tile_tap [p_pad/256] int32
+ * gives the tap of every 256-row tile (every tap segment is padded to 256 rows).  cin, cout multiples of 16 / 32.
+ * Persistent CTAs, 256-row tiles: two M=128 accumulators share every W stage. */
 int ss_subm_conv_gemm256(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
                          int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream);
 
-/* Third generation of the same stage on CTA pairs (tcgen05 cta_group::2, csrc/conv_gemm3.cu): identical arguments and
+/* The same stage on CTA pairs (tcgen05 cta_group::2, csrc/conv_gemm3.cu): identical arguments and
  * results; cout >= 256 (the 256-column slab is split between the two CTAs).  Double-buffered TMEM accumulators: the
  * store of tile i overlaps the MMAs of tile i + 1. */
 int ss_subm_conv_gemm_pair(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,

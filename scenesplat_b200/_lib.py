@@ -33,7 +33,6 @@ SIGNATURES = {
     "ss_kmap_build": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ss_kmap_pairs": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "ss_subm_conv_simt": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _i, _vp]),
-    "ss_subm_conv_gemm": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "ss_subm_conv_gemm256": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "ss_subm_conv_gemm_pair": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "ss_subm_conv_reduce": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp]),

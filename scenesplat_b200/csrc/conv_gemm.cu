@@ -1,17 +1,13 @@
-// Submanifold convolution on the 5th-gen tensor cores: gather-GEMM over compacted (input, output)
-// pairs grouped by tap, fp32 accumulation in TMEM, then a gather-sum over taps.
+// Language head on the 5th-gen tensor cores + the gather-sum stage of the submanifold convolution.
 //
-// Replaces (reference): spconv.SubMConv3d forward for the xCPE 3^3 convs
-// (point_transformer_v3m1_base.py:277-284; fp32 in the reference, bf16 x bf16 -> fp32 here).
-//
-// Stage 1 (gather_gemm_kernel): product row r (tap t = tile_tap[r/128]) = X[pair_in[r], :] @ W_t^T.
-//   CTA = 128 product rows x BN output channels.  Warps 0-3 gather the A rows with 16-byte cp.async
-//   into a 128B-swizzled K-major tile (8 lanes cover one 128-byte row segment -> full-line requests),
-//   warp 4 streams the W_t tile with TMA, warp 5 issues tcgen05.mma (M=128, N=BN, K=16) into TMEM;
-//   warps 0-3 then drain TMEM (tcgen05.ld) to bf16.  Only ACTIVE pairs are multiplied: FLOPs =
-//   2 * pairs * Cin * Cout (an output-stationary dense-tap kernel would do 27/7.2 = 3.75x more on
-//   surface data).  2 CTAs are co-resident per SM so one CTA's epilogue overlaps the other's main loop.
-// Stage 2 (conv_reduce_kernel): out[p, :] = bias + sum_t prod[ypos[t][p], :]  (HBM-bound gather-sum).
+// (1) head_gemm_kernel: logits = feat @ T^T (T = <= 256 text embeddings) with sigmoid + max / argmax (EPI = 1) or
+//     probability accumulation (EPI = 2) fused into the TMEM epilogue, so the N x K logits never reach HBM.
+//     Replaces (reference): pointcept/engines/hooks/evaluator.py:793-800, pointcept/engines/test.py:335-349.
+//     CTA = 128 feature rows x 256 classes.  Warps 0-3 stage the A rows with 16-byte cp.async into a 128B-swizzled
+//     K-major tile, warp 4 streams the T tile with TMA, warp 5 issues tcgen05.mma (M=128, N=256, K=16) into TMEM,
+//     warps 0-3 then drain TMEM (tcgen05.ld).
+// (2) conv_reduce_kernel: out[p, :] = bias + sum_t prod[ypos[t][p], :], the HBM-bound second stage of the xCPE conv
+//     (first stage: the gather-GEMMs of conv_gemm2.cu / conv_gemm3.cu).
 #include "tc_common.cuh"
 #include "../../include/scenesplat_b200.h"
 
@@ -43,9 +39,8 @@ struct HeadEpi {
 
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads)
-gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restrict__ pair_in,
-                   const __grid_constant__ CUtensorMap tmap_w, const int32_t* __restrict__ tile_tap, int cin, int cout,
-                   __nv_bfloat16* __restrict__ prod, HeadEpi head) {
+head_gemm_kernel(const __nv_bfloat16* __restrict__ X, const __grid_constant__ CUtensorMap tmap_w, int cin,
+                 HeadEpi head) {
   using S = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -57,17 +52,11 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably uniform
   const int tile = blockIdx.x;
-  const int n0 = blockIdx.y * BN;
-  const int tap = EPI == 0 ? tile_tap[tile] : 0;
   const int nk = (cin + kBK - 1) / kBK;
 
-  if (threadIdx.x < kTileM) {
-    if (EPI == 0) {
-      s_rows[threadIdx.x] = pair_in[(size_t)tile * kTileM + threadIdx.x];
-    } else {  // identity rows, clamped (rows past n_rows are computed but never written)
-      const int64_t r = (int64_t)tile * kTileM + threadIdx.x;
-      s_rows[threadIdx.x] = (int32_t)(r < head.n_rows ? r : head.n_rows - 1);
-    }
+  if (threadIdx.x < kTileM) {  // identity rows, clamped (rows past n_rows are computed but never written)
+    const int64_t r = (int64_t)tile * kTileM + threadIdx.x;
+    s_rows[threadIdx.x] = (int32_t)(r < head.n_rows ? r : head.n_rows - 1);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -109,56 +98,35 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
     tc::tc_fence_after();
     const int row = warp * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    if constexpr (EPI != 0) {
-      const int64_t grow = (int64_t)tile * kTileM + row;
-      float best = -INFINITY;
-      int arg = 0;
-      float* prow = nullptr;
-      if (EPI == 2 && grow < head.n_rows)
-        prow = head.probs_accum + (size_t)(head.idx ? head.idx[grow] : grow) * head.n_classes;
-#pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
-        if (j * 32 >= head.n_classes) break;
-        uint32_t v[32];
-        tc::tmem_ld32(t_lane + j * 32, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          const int k = j * 32 + u;
-          const float lg = __uint_as_float(v[u]);
-          if (k < head.n_classes) {
-            if (EPI == 1) {
-              if (lg > best) { best = lg; arg = k; }
-            } else if (prow) {
-              prow[k] += 1.f / (1.f + __expf(-lg));
-            }
-          }
-        }
-      }
-      if (EPI == 1 && grow < head.n_rows) {
-        const float pr = 1.f / (1.f + __expf(-best));
-        head.max_prob[grow] = pr;
-        head.label[grow] = pr < head.threshold ? -1 : arg;
-      }
-    } else {
-    __nv_bfloat16* orow = prod + ((size_t)tile * kTileM + row) * cout + n0;
+    const int64_t grow = (int64_t)tile * kTileM + row;
+    float best = -INFINITY;
+    int arg = 0;
+    float* prow = nullptr;
+    if (EPI == 2 && grow < head.n_rows)
+      prow = head.probs_accum + (size_t)(head.idx ? head.idx[grow] : grow) * head.n_classes;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
-      if (n0 + j * 32 >= cout) break;
+      if (j * 32 >= head.n_classes) break;
       uint32_t v[32];
       tc::tmem_ld32(t_lane + j * 32, v);
       tc::tmem_ld_wait();
-      uint4* dst = reinterpret_cast<uint4*>(orow + j * 32);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        uint4 o;
-        o.x = tc::pack_bf16(__uint_as_float(v[u * 8 + 0]), __uint_as_float(v[u * 8 + 1]));
-        o.y = tc::pack_bf16(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3]));
-        o.z = tc::pack_bf16(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5]));
-        o.w = tc::pack_bf16(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7]));
-        dst[u] = o;
+      for (int u = 0; u < 32; ++u) {
+        const int k = j * 32 + u;
+        const float lg = __uint_as_float(v[u]);
+        if (k < head.n_classes) {
+          if (EPI == 1) {
+            if (lg > best) { best = lg; arg = k; }
+          } else if (prow) {
+            prow[k] += 1.f / (1.f + __expf(-lg));
+          }
+        }
       }
     }
+    if (EPI == 1 && grow < head.n_rows) {
+      const float pr = 1.f / (1.f + __expf(-best));
+      head.max_prob[grow] = pr;
+      head.label[grow] = pr < head.threshold ? -1 : arg;
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ B producer (TMA, one lane)
@@ -167,8 +135,7 @@ gather_gemm_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restric
         const int s = kc % STAGES, it = kc / STAGES;
         tc::mbar_wait(&empty_bar[s], (it & 1) ^ 1);
         tc::mbar_arrive_expect_tx(&full_bar[s], S::kBBytes);
-        tc::tma_load_2d(tc::smem_u32(smem + s * S::kStageBytes + S::kABytes), &tmap_w, kc * kBK, tap * cout + n0,
-                        &full_bar[s]);
+        tc::tma_load_2d(tc::smem_u32(smem + s * S::kStageBytes + S::kABytes), &tmap_w, kc * kBK, 0, &full_bar[s]);
       }
     }
   } else {
@@ -276,28 +243,14 @@ conv_reduce_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __rest
   }
 }
 
-template <int BN, int STAGES>
-static int launch_gather_gemm(const void* X, const int32_t* pair_in, const CUtensorMap& tmap, const int32_t* tile_tap,
-                              int64_t tiles, int cin, int cout, void* prod, cudaStream_t stream) {
-  using S = GemmSmem<BN, STAGES>;
-  auto kern = gather_gemm_kernel<BN, STAGES, 0>;
-  SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-  dim3 grid((unsigned)tiles, (unsigned)((cout + BN - 1) / BN));
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>((const __nv_bfloat16*)X, pair_in, tmap, tile_tap, cin, cout,
-                                                  (__nv_bfloat16*)prod, HeadEpi{});
-  SS_CHECK_LAUNCH();
-  return SS_OK;
-}
-
 template <int EPI>
 static int launch_head(const void* feat, const CUtensorMap& tmap, int64_t n, int channels, const HeadEpi& head,
                        cudaStream_t stream) {
   using S = GemmSmem<256, 2>;
-  auto kern = gather_gemm_kernel<256, 2, EPI>;
+  auto kern = head_gemm_kernel<256, 2, EPI>;
   SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   dim3 grid((unsigned)ceil_div64(n, kTileM), 1);
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>((const __nv_bfloat16*)feat, nullptr, tmap, nullptr, channels, 256,
-                                                  nullptr, head);
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>((const __nv_bfloat16*)feat, tmap, channels, head);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
@@ -322,27 +275,6 @@ int ss_lang_head_tc(const void* feat_bf16, const void* text_bf16, int64_t n, int
   ss::HeadEpi head{n, n_classes, threshold, max_prob, label, probs_accum, idx};
   return mode == 0 ? ss::launch_head<1>(feat_bf16, tmap, n, channels, head, stream)
                    : ss::launch_head<2>(feat_bf16, tmap, n, channels, head, stream);
-}
-
-int ss_subm_conv_gemm(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
-                      int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (k3 < 1 || p_pad < 0 || p_pad % ss::kTileM != 0 || cin < 16 || cin % 16 != 0 || cout < 32 || cout % 32 != 0) return SS_BAD_ARGS;
-  if (p_pad == 0) return SS_OK;
-  if (!in_bf16 || !pair_in || !w_bf16 || !tile_tap || !prod_bf16) return SS_BAD_ARGS;
-  if (((uintptr_t)in_bf16 | (uintptr_t)w_bf16 | (uintptr_t)prod_bf16) % 16 != 0) return SS_BAD_ARGS;
-  const int64_t tiles = p_pad / ss::kTileM;
-  const int bn = cout >= 256 ? 256 : (cout > 64 ? 128 : (cout > 32 ? 64 : 32));
-  // W viewed as one [k3 * cout, cin] K-major matrix; rows past the last tap read as zero (TMA OOB fill)
-  CUtensorMap tmap;
-  int rc = ss::make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)k3 * cout, (uint64_t)cin, (uint32_t)bn, ss::kBK);
-  if (rc) return rc;
-  switch (bn) {
-    case 256: return ss::launch_gather_gemm<256, 2>(in_bf16, pair_in, tmap, tile_tap, tiles, cin, cout, prod_bf16, stream);
-    case 128: return ss::launch_gather_gemm<128, 3>(in_bf16, pair_in, tmap, tile_tap, tiles, cin, cout, prod_bf16, stream);
-    case 64: return ss::launch_gather_gemm<64, 4>(in_bf16, pair_in, tmap, tile_tap, tiles, cin, cout, prod_bf16, stream);
-    default: return ss::launch_gather_gemm<32, 4>(in_bf16, pair_in, tmap, tile_tap, tiles, cin, cout, prod_bf16, stream);
-  }
 }
 
 int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float* bias, int64_t n, int k3, int cout,

@@ -1,0 +1,154 @@
+"""Callers of the hot path at scene scale (SURVEY.md section 8, rows g1 / g3 of VERDICT.md):
+
+  zero_shot_scene       the per-scene flow of pointcept/engines/test.py:300-383 + hooks/evaluator.py:785-834 on the
+                        device: GridSample(test) fragments -> LangPretrainer(chunk_size) per fragment ->
+                        pred[idx] += sigmoid(feat T^T) (fused head) -> max / argmax / threshold -> k-NN vote ->
+                        confusion-matrix update.
+  chunk_origins / scene_chunks
+                        the chunking rule of pointcept/datasets/preprocessing/sampling_chunking_data_gs.py:84-125
+                        (6 m x 6 m windows on a 3 m stride in the bird's-eye view, windows with too few points dropped).
+  sharded_chunk_labels  chunk-sharded multi-GPU inference: every rank runs the chunks
+                        `sharding.assign_chunks` gives it through `ChunkPipeline`; the only exchange is ONE all_gather
+                        of the int32 labels.  No data-path collective.
+
+Everything here is host orchestration over the package's kernels; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import sharding
+from .lang import ChunkPipeline, zero_shot_accumulate, zero_shot_labels
+from .transform import GridSample
+from .voting import confusion_update, neighbor_voting
+
+ATTR_KEYS = ("coord", "color", "opacity", "quat", "scale")
+
+
+def feat_of(d):
+    """feat = cat(color, opacity, quat, scale): the 11 input channels of the lang configs
+    (configs/scannet/lang-pretrain-scannet-mcmc-wo-normal-contrastive.py:171)."""
+    return torch.cat([d["color"], d["opacity"], d["quat"], d["scale"]], 1).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- zero-shot scene
+def zero_shot_scene(model, scene, text, gt=None, grid_size=0.02, chunk_size=600000, k_vote=25, ignore_index=-1,
+                    threshold=0.1, timings=None):
+    """scene: dict of device tensors (coord [N,3] f32, color, opacity, quat, scale); text: [K,768] unit rows.
+    Returns (labels [N] int64 after neighbour voting, confusion [K,K] int64 or None).  `timings` (a dict) receives
+    wall-clock seconds per stage (each stage bracketed by a device synchronize) when given."""
+    dev = scene["coord"].device
+    n_raw, K = scene["coord"].shape[0], text.shape[0]
+
+    def stage(name, t0):
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            timings[name] = timings.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
+    if timings is not None:
+        torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    gs = GridSample(grid_size=grid_size, hash_type="fnv", mode="test", keys=ATTR_KEYS, return_grid_coord=True, device=dev)
+    parts = gs(dict(scene))
+    t0 = stage("gridsample_fragments", t0)
+    pred = torch.zeros((n_raw, K), device=dev)
+    n_fwd = 0
+    with torch.no_grad():
+        for p in parts:
+            n = p["coord"].shape[0]
+            inp = dict(coord=p["coord"], grid_coord=p["grid_coord"], feat=feat_of(p),
+                       offset=torch.tensor([n], device=dev))
+            feat = model(inp, chunk_size=chunk_size)["point_feat"]["feat"]
+            zero_shot_accumulate(pred, feat, text, p["index"])
+            n_fwd += n
+    t0 = stage("fragments_forward_head", t0)
+    mx, arg = torch.max(pred, dim=1)
+    arg[mx < threshold] = ignore_index
+    t0 = stage("argmax", t0)
+    voted = neighbor_voting(scene["coord"], arg, k_vote, ignore_index, K) if k_vote else arg
+    t0 = stage("neighbor_voting", t0)
+    conf = None
+    if gt is not None:
+        conf = torch.zeros((K, K), dtype=torch.int64, device=dev)
+        fn_ignore = torch.zeros(K, dtype=torch.int64, device=dev)
+        confusion_update(gt, voted, K, ignore_index, conf, fn_ignore)
+        stage("confusion", t0)
+    if timings is not None:
+        timings["fragments"] = len(parts)
+        timings["voxels_forwarded"] = n_fwd
+    return voted, conf
+
+
+# ----------------------------------------------------------------------------------------------- chunk rule
+def chunk_origins(xy_max, chunk_range=(6.0, 6.0), chunk_stride=(3.0, 3.0)):
+    """Window origins (x0, y0): np.arange(0, max + stride - range, stride) per axis, "ij" order
+    (sampling_chunking_data_gs.py:84-92; rooms smaller than range - stride yield no window, as there)."""
+    xs = np.arange(0, float(xy_max[0]) + chunk_stride[0] - chunk_range[0], chunk_stride[0])
+    ys = np.arange(0, float(xy_max[1]) + chunk_stride[1] - chunk_range[1], chunk_stride[1])
+    x, y = np.meshgrid(xs, ys, indexing="ij")
+    return np.stack([x.reshape(-1), y.reshape(-1)], 1)
+
+
+def scene_chunks(coord, chunk_range=(6.0, 6.0), chunk_stride=(3.0, 3.0), chunk_minimum_size=10000):
+    """-> list of int64 index tensors (device), one per kept window: points with x in [x0, x0 + range_x) and
+    y in [y0, y0 + range_y); windows with fewer than `chunk_minimum_size` points are dropped (:113-125)."""
+    xy_max = coord[:, :2].max(0).values.tolist()
+    out = []
+    for x0, y0 in chunk_origins(xy_max, chunk_range, chunk_stride):
+        m = ((coord[:, 0] >= x0) & (coord[:, 0] < x0 + chunk_range[0]) &
+             (coord[:, 1] >= y0) & (coord[:, 1] < y0 + chunk_range[1]))
+        idx = m.nonzero(as_tuple=True)[0]
+        if idx.numel() >= chunk_minimum_size:
+            out.append(idx)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- sharded sweep
+def sharded_chunk_labels(model, chunks, text, rank=0, world=1, policy="lpt", group=None, gather=True):
+    """chunks: list of dicts (coord, grid_coord, feat, offset) -- pinned host or device tensors; every rank holds the
+    same list (or at least the same sizes) and runs only its share.  Returns (labels per chunk: list of int32 tensors
+    for ALL chunks when gather=True else only this rank's, stats dict with this rank's device ms and voxel count)."""
+    sizes = [int(c["coord"].shape[0]) for c in chunks]
+    table = sharding.assign_chunks(sizes, world, policy)
+    mine = table[rank]
+    dev = next(model.parameters()).device
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    labels = {}
+    pipe = ChunkPipeline(model, dev)
+    e0.record()
+    for i, feat in zip(mine, pipe.map(chunks[i] for i in mine)):
+        _, lab = zero_shot_labels(feat, text)
+        labels[i] = lab.int()
+    e1.record()
+    pipe.flush()
+    e1.synchronize()
+    stats = dict(ms=e0.elapsed_time(e1), voxels=sum(sizes[i] for i in mine), chunks=len(mine), table=table)
+    if not gather or world == 1:
+        return [labels.get(i) for i in range(len(chunks))], stats
+    import torch.distributed as dist
+    # one exchange: every rank contributes its labels packed back to back, padded to the largest share
+    cap = max(sum(sizes[i] for i in t) for t in table)
+    buf = torch.full((cap,), -2, dtype=torch.int32, device=dev)
+    o = 0
+    for i in mine:
+        buf[o:o + sizes[i]] = labels[i]
+        o += sizes[i]
+    allbuf = torch.empty((world, cap), dtype=torch.int32, device=dev)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    dist.all_gather_into_tensor(allbuf, buf, group=group)
+    g1.record()
+    g1.synchronize()
+    stats["all_gather_ms"] = g0.elapsed_time(g1)
+    stats["all_gather_bytes"] = int(allbuf.numel() * 4)
+    out = [None] * len(chunks)
+    for r, t in enumerate(table):
+        o = 0
+        for i in t:
+            out[i] = allbuf[r, o:o + sizes[i]]
+            o += sizes[i]
+    return out, stats

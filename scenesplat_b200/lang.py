@@ -231,10 +231,17 @@ class ChunkPipeline(object):
         main = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.side):
             d = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in chunk.items()}
+            for v in d.values():
+                # Memory made here belongs to the side stream's allocator pool, but the feature phase reads it on
+                # `main`: tell the allocator, so a block is never handed to the next chunk's copy while a kernel of
+                # this chunk still has to read it (the input `feat` loses its last host reference the moment
+                # Embedding.forward rebinds point.feat, long before the stem conv has run).
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    v.record_stream(main)
             point = self.model.prepare(d)
             ev = torch.cuda.Event()
             ev.record(self.side)
-        return point, ev, main
+        return point, d, ev, main
 
     def map(self, chunks):
         it = iter(chunks)
@@ -243,23 +250,25 @@ class ChunkPipeline(object):
         except StopIteration:
             return
         while nxt is not None:
-            point, ev, main = nxt
+            point, inputs, ev, main = nxt
             main.wait_event(ev)
             with torch.no_grad():
                 out = self.model.features_prepared(point)
             done = torch.cuda.Event()
             done.record(main)
-            self._keep.append((point, done))
+            # the prepared Point AND the chunk's device inputs stay referenced until `done` has completed
+            self._keep.append((point, inputs, done))
             try:
                 nxt = self._stage1(next(it))  # overlaps the feature phase just enqueued
             except StopIteration:
                 nxt = None
             while len(self._keep) > 2:  # memory made on the side stream is released only after its last use
-                _, old = self._keep.pop(0)
-                old.synchronize()
+                ent = self._keep.pop(0)
+                ent[-1].synchronize()
+                del ent
             yield out["feat"]
 
     def flush(self):
-        for _, ev in self._keep:
-            ev.synchronize()
+        for ent in self._keep:
+            ent[-1].synchronize()
         self._keep.clear()

@@ -5,8 +5,6 @@ computation itself (the CUDA library is the only implementation).
 """
 from __future__ import annotations
 
-import os
-
 import torch
 
 from . import _lib as L
@@ -131,8 +129,10 @@ def pool_index(code, order, grid_coord, batch, pooling_depth: int, src_row):
     cgc = torch.empty((n, 3), dtype=torch.int64, device=dev) if gc is not None else None
     cb = torch.empty(n, dtype=torch.int64, device=dev) if batch is not None else None
     ws = L.workspace(L.load().ss_pool_workspace_bytes(n), dev)
-    L.call("ss_pool_index", L.ptr(code.contiguous()), L.ptr(order.contiguous()), L.ptr(gc),
-           L.ptr(batch.contiguous() if batch is not None else None), n, k, pooling_depth, L.int_array(src_row), n,
+    code_c, order_c = code.contiguous(), order.contiguous()  # bound to names: they must outlive the launch
+    batch_c = batch.contiguous() if batch is not None else None
+    L.call("ss_pool_index", L.ptr(code_c), L.ptr(order_c), L.ptr(gc),
+           L.ptr(batch_c), n, k, pooling_depth, L.int_array(src_row), n,
            L.ptr(cluster), L.ptr(seg_start), L.ptr(head), L.ptr(m_dev), L.ptr(ccode), L.ptr(corder), L.ptr(cinv),
            L.ptr(cgc), L.ptr(cb), L.ptr(ws), ws.numel(), L.stream(), meta=_POOL_META)
     m = int(m_dev.item())
@@ -183,8 +183,9 @@ def kmap_build(grid_coord, batch, code_row, order_row, depth: int, order_id: int
     nbr = torch.empty((k3, n), dtype=torch.int32, device=dev)
     cnt = torch.empty(k3, dtype=torch.int64, device=dev)
     ws = L.workspace(L.load().ss_kmap_workspace_bytes(n, k), dev)
-    L.call("ss_kmap_build", L.ptr(g), int(g.dtype == torch.int32), L.ptr(batch.contiguous()),
-           L.ptr(code_row.contiguous()), L.ptr(order_row.contiguous()), n, depth, order_id, k, L.ptr(nbr), L.ptr(cnt),
+    batch_c, code_c, order_c = batch.contiguous(), code_row.contiguous(), order_row.contiguous()
+    L.call("ss_kmap_build", L.ptr(g), int(g.dtype == torch.int32), L.ptr(batch_c),
+           L.ptr(code_c), L.ptr(order_c), n, depth, order_id, k, L.ptr(nbr), L.ptr(cnt),
            L.ptr(ws), ws.numel(), L.stream())
     return nbr, cnt
 
@@ -199,8 +200,7 @@ def upload(values, dtype, device):
     return t.pin_memory().to(device, non_blocking=True)
 
 
-CONV_PAIR = int(os.environ.get("SS_CONV_PAIR", "1"))  # developer A/B switch: 0 = single-CTA 256-row kernel for every width
-CONV_TILE = int(os.environ.get("SS_CONV_TILE", "256"))  # rows per gather-GEMM tile (128: first-generation kernel)
+CONV_TILE = 256  # rows per gather-GEMM tile (one CTA pair = 2 x 128, or one CTA with two accumulators)
 
 
 def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = None):
@@ -220,7 +220,8 @@ def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = None):
     pair_in = torch.empty(max(p_pad, 1), dtype=torch.int32, device=dev)
     ypos = torch.empty((k3, n), dtype=torch.int32, device=dev)
     ws = L.workspace(L.load().ss_kmap_workspace_bytes(n, k), dev)
-    L.call("ss_kmap_pairs", L.ptr(nbr), L.ptr(order_row.contiguous()), n, k, L.ptr(base_dev), p_pad, L.ptr(pair_in),
+    order_c = order_row.contiguous()
+    L.call("ss_kmap_pairs", L.ptr(nbr), L.ptr(order_c), n, k, L.ptr(base_dev), p_pad, L.ptr(pair_in),
            L.ptr(ypos), L.ptr(ws), ws.numel(), L.stream())
     return dict(pair_in=pair_in, ypos=ypos, tile_tap=upload(tile_tap or [0], torch.int32, dev),
                 p_pad=p_pad, pairs=int(sum(int(c) for c in tap_count_host)), tile=tile, tap_base=list(base),
@@ -238,14 +239,17 @@ def subm_conv_simt(x, nbr, wt, bias=None, scale=None, shift=None, act=0, out_dty
     return out
 
 
-def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16):
-    """tcgen05 gather-GEMM (+ gather-sum).  w_bf16: [k^3, cout, cin] bf16."""
+def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16, impl="auto"):
+    """tcgen05 gather-GEMM (+ gather-sum).  w_bf16: [k^3, cout, cin] bf16.  impl: "auto" = CTA pairs for cout >= 256
+    (csrc/conv_gemm3.cu), the single-CTA two-accumulator kernel below that (csrc/conv_gemm2.cu); "single" / "pair"
+    force one of them (they are bit-identical; tests compare them)."""
     k3, cout, cin = w_bf16.shape
     p_pad = pairs["p_pad"]
+    if pairs.get("tile") != CONV_TILE:
+        raise L.CudaKernelError("pair lists must be padded to %d-row tiles (ops.kmap_pairs)" % CONV_TILE)
     prod = torch.empty((max(p_pad, 1), cout), dtype=_BF16, device=x_bf16.device)
-    fn = "ss_subm_conv_gemm256" if pairs.get("tile", 128) == 256 else "ss_subm_conv_gemm"
-    if fn == "ss_subm_conv_gemm256" and CONV_PAIR and cout >= 256:
-        fn = "ss_subm_conv_gemm_pair"  # CTA pairs, double-buffered accumulators (csrc/conv_gemm3.cu)
+    pair = cout >= 256 if impl == "auto" else impl == "pair"
+    fn = "ss_subm_conv_gemm_pair" if pair else "ss_subm_conv_gemm256"
     L.call(fn, L.ptr(x_bf16.contiguous()), L.ptr(pairs["pair_in"]), L.ptr(w_bf16),
            L.ptr(pairs["tile_tap"]), p_pad, k3, cin, cout, L.ptr(prod), L.stream(),
            meta=dict(flops=2.0 * pairs["pairs"] * cin * cout, bytes=2.0 * pairs["pairs"] * (cin + cout)))
@@ -363,7 +367,8 @@ def subm_conv_wgrad(x_bf16, dy_bf16, pairs, pair_out, k3, rows_per_chunk=8192):
         pairs[key] = upload(rows or [(0, 0, 0, 0)], torch.int32, x_bf16.device), len(rows)
     chunks, n_chunks = pairs[key]
     dw = torch.zeros((k3, cout, cin), dtype=torch.float32, device=x_bf16.device)
-    L.call("ss_subm_conv_wgrad", L.ptr(x_bf16.contiguous()), L.ptr(dy_bf16.contiguous()), L.ptr(pairs["pair_in"]),
+    x_bf16, dy_bf16 = x_bf16.contiguous(), dy_bf16.contiguous()
+    L.call("ss_subm_conv_wgrad", L.ptr(x_bf16), L.ptr(dy_bf16), L.ptr(pairs["pair_in"]),
            L.ptr(pair_out), L.ptr(chunks), n_chunks, k3, cin, cout, L.ptr(dw), L.stream(),
            meta=dict(flops=2.0 * pairs["pairs"] * cin * cout))
     return dw
@@ -494,6 +499,7 @@ def class_half_sums(pred, mask, segment, half, n_classes: int):
     n, c = pred.shape
     sums = torch.empty((n_classes * 2, c), dtype=torch.float32, device=pred.device)
     counts = torch.empty(n_classes * 2, dtype=torch.int32, device=pred.device)
-    L.call("ss_class_half_sums", L.ptr(pred), _isbf(pred), L.ptr(m8), L.ptr(_i64(segment).contiguous()),
-           L.ptr(_i64(half).contiguous()), n, c, n_classes, L.ptr(sums), L.ptr(counts), L.stream())
+    seg64, half64 = _i64(segment).contiguous(), _i64(half).contiguous()  # two live tensors: never the same block
+    L.call("ss_class_half_sums", L.ptr(pred), _isbf(pred), L.ptr(m8), L.ptr(seg64),
+           L.ptr(half64), n, c, n_classes, L.ptr(sums), L.ptr(counts), L.stream())
     return sums, counts

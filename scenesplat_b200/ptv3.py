@@ -55,23 +55,29 @@ class DropPath(nn.Module):
 def _no_training(mod):
     if torch.is_grad_enabled() and mod.training:
         raise NotImplementedError(
-            "scenesplat_b200: the training path (backward kernels) is not built yet; call .eval() and use "
-            "torch.no_grad() / torch.inference_mode() (SURVEY.md section 8f, row 1)")
+            f"scenesplat_b200: {type(mod).__name__}.forward is the inference path (fused, no autograd graph).  "
+            "Training runs through PointTransformerV3.forward / LangPretrainer.forward, which route to "
+            "scenesplat_b200/training.py; to call a sub-module on its own use .eval() and torch.no_grad()")
 
 
 class _Cache:
-    """bf16 / folded copies of parameters, refreshed when the parameter is modified or reloaded."""
+    """bf16 / folded copies of parameters, refreshed when a parameter is modified in place or rebound (load_state_dict,
+    `.to()`).  The copies live ON the owning module (a plain attribute, not a buffer: never in `state_dict`), so they
+    are freed with the model and can never be served to another one."""
 
-    def __init__(self):
-        self.store = {}
+    ATTR = "_ss_prepared"
 
-    def get(self, key, params, fn):
+    def get(self, owner, key, params, fn):
+        store = owner.__dict__.get(self.ATTR)
+        if store is None:
+            store = {}
+            object.__setattr__(owner, self.ATTR, store)
         ver = tuple((p._version, p.data_ptr()) for p in params)
-        ent = self.store.get(key)
+        ent = store.get(key)
         if ent is None or ent[0] != ver:
             with torch.no_grad():
                 ent = (ver, fn())
-            self.store[key] = ent
+            store[key] = ent
         return ent[1]
 
 
@@ -80,7 +86,7 @@ _cache = _Cache()
 
 def linear_bf16(lin: nn.Linear, x):
     """Library GEMM (cuBLASLt) in bf16, fp32 accumulate."""
-    w, b = _cache.get(("lin", id(lin)), [lin.weight] + ([lin.bias] if lin.bias is not None else []),
+    w, b = _cache.get(lin, "lin", [lin.weight] + ([lin.bias] if lin.bias is not None else []),
                       lambda: (lin.weight.detach().to(BF16).contiguous(),
                                lin.bias.detach().to(BF16).contiguous() if lin.bias is not None else None))
     if x.dtype != BF16:
@@ -111,11 +117,11 @@ def cpe_folded(conv, lin: nn.Linear):
             b = b + wl @ conv.bias.detach().float()
         return w, b.contiguous()
     deps = [conv.weight, lin.weight] + [t for t in (conv.bias, lin.bias) if t is not None]
-    return _cache.get(("cpe", id(conv), id(lin)), deps, fn)
+    return _cache.get(lin, "cpe", deps, fn)
 
 
 def ln_params(ln: nn.LayerNorm):
-    return _cache.get(("ln", id(ln)), [ln.weight, ln.bias],
+    return _cache.get(ln, "ln", [ln.weight, ln.bias],
                       lambda: (ln.weight.detach().float().clone(), ln.bias.detach().float().clone()))  # own, aligned storage
 
 
@@ -125,7 +131,7 @@ def bn_fold(bn: nn.BatchNorm1d):
         scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
         shift = bn.bias.detach().float() - bn.running_mean.float() * scale
         return scale.contiguous(), shift.contiguous()
-    return _cache.get(("bn", id(bn)), [bn.weight, bn.bias, bn.running_mean, bn.running_var], fn)
+    return _cache.get(bn, "bn", [bn.weight, bn.bias, bn.running_mean, bn.running_var], fn)
 
 
 def _single(seq, cls):
@@ -248,7 +254,7 @@ class MLP(nn.Module):
         exact_gelu = isinstance(self.act, nn.GELU) and self.act.approximate == "none"
         if exact_gelu and x.is_cuda and fc1.in_features % 16 == 0 and fc1.out_features % 32 == 0:
             # fc1 + bias + GELU as ONE kernel on CTA pairs (csrc/gemm2cta.cu): the N x 4C hidden is written once
-            w, b = _cache.get(("lin_act", id(fc1)), [fc1.weight] + ([fc1.bias] if fc1.bias is not None else []),
+            w, b = _cache.get(fc1, "lin_act", [fc1.weight] + ([fc1.bias] if fc1.bias is not None else []),
                               lambda: (fc1.weight.detach().to(BF16).contiguous(),
                                        fc1.bias.detach().float().clone() if fc1.bias is not None else None))
             h = ops.linear_act(x if x.dtype == BF16 else x.to(BF16), w, b, act=1)

@@ -238,17 +238,14 @@ class SegmentMeanFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------ model walk
-_BF16_PARAMS = {}
-
-
 def _bf16_param(p):
-    """bf16 copy of a parameter, made once per optimiser step (keyed on the tensor's version counter)."""
-    key = id(p)
-    ent = _BF16_PARAMS.get(key)
+    """bf16 copy of a parameter, made once per optimiser step (refreshed when the tensor's version counter or storage
+    changes).  Kept on the parameter object itself, so it dies with the model (no process-global table)."""
+    ent = p.__dict__.get("_ss_bf16")
     ver = (p._version, p.data_ptr())
     if ent is None or ent[0] != ver:
         ent = (ver, p.detach().to(BF16))
-        _BF16_PARAMS[key] = ent
+        p.__dict__["_ss_bf16"] = ent
     return ent[1]
 
 
