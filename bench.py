@@ -21,6 +21,7 @@ Extra keys measured in the same run (BASELINE.json configs 1, 3, 4, 5 and the sa
 from __future__ import annotations
 
 import argparse
+import contextlib
 import gc
 import json
 import os
@@ -284,8 +285,13 @@ def main():
     # Allocator pre-warm (setup, not part of any step): reserve the step's working set once so the timed region never
     # waits for the driver to map memory.  The block goes back to torch's caching allocator and is carved up by the
     # forwards; nothing computed is cached.
-    pre = torch.empty(24 << 30, dtype=torch.uint8, device=dev)
-    del pre
+    def reserve(nbytes, stream=None):
+        """torch's caching allocator keeps one pool per stream: reserve on the stream that will allocate."""
+        with torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext():
+            blk = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            del blk
+
+    reserve(40 << 30)
 
     model = build_model().to(dev)
     text = torch.nn.functional.normalize(torch.randn(200, 768, generator=torch.Generator().manual_seed(1)), dim=1).to(dev)
@@ -313,8 +319,11 @@ def main():
                 mx, lab = S.zero_shot_labels(feat, text)
                 return lab.to("cpu", non_blocking=True), mx.to("cpu", non_blocking=True)
     else:
-        gen_resident = S.ChunkPipeline(model, dev).map(forever(dev_in))
-        gen_e2e = S.ChunkPipeline(model, dev).map(forever(host_in))
+        pipe_resident, pipe_e2e = S.ChunkPipeline(model, dev), S.ChunkPipeline(model, dev)
+        for p in (pipe_resident, pipe_e2e):
+            reserve(6 << 30, p.side)  # index phase + input copies of the chunks in flight
+        gen_resident = pipe_resident.map(forever(dev_in))
+        gen_e2e = pipe_e2e.map(forever(host_in))
 
         def step_resident():
             flush.zero_()
@@ -353,6 +362,7 @@ def main():
         L.PROFILE = {} if profile is not None else None
         L.PROFILE_ONLY = profile if isinstance(profile, (set, frozenset)) else None
         l0 = L.launch_count()
+        mem0 = torch.cuda.memory_stats(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         marks, cpu_ms = [], []
@@ -375,10 +385,17 @@ def main():
         clocks = sampler.stop() if sampler else None
         rank_ms = gather_ranks(ms / steps)
         rank_host = gather_ranks(float(np.median(cpu_ms)))
+        mem1 = torch.cuda.memory_stats(dev)
         stats = dict(p50=float(np.percentile(per, 50)), p95=float(np.percentile(per, 95)), min=float(min(per)),
-                     max=float(max(per)), host_enqueue_ms_p50=float(np.median(cpu_ms)),
+                     max=float(max(per)), per_step_ms=[round(v, 2) for v in per],
+                     host_loop_ms_p50=float(np.median(cpu_ms)),
+                     allocator=dict(reserved_gib=round(mem1["reserved_bytes.all.current"] / 2 ** 30, 2),
+                                    reserved_growth_gib=round((mem1["reserved_bytes.all.current"] -
+                                                               mem0["reserved_bytes.all.current"]) / 2 ** 30, 3),
+                                    segment_allocs=int(mem1["num_device_alloc"] - mem0["num_device_alloc"])),
                      per_rank_ms_per_step=[round(v, 3) for v in rank_ms],
-                     per_rank_host_enqueue_ms=[round(v, 3) for v in rank_host])
+                     per_rank_host_loop_ms=[round(v, 3) for v in rank_host],
+                     note="host_loop_ms = host time per loop iteration (enqueue + the pipeline's wait for chunk i - 2)")
         return max(rank_ms) * steps, prof, launches, clocks, stats
 
     hot = frozenset({"ss_patch_attention", "ss_subm_conv_gemm256", "ss_subm_conv_gemm_pair"})  # the two candidates for "dominant own kernel"

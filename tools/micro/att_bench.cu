@@ -1,7 +1,8 @@
-// Stand-alone driver of the tcgen05 patch-attention kernel (developer tool): timing at a given shape and,
-// when built with -DSS_ATT_TRACE, per-CTA clock64 traces of the pipeline phases.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -lineinfo [-DSS_ATT_TRACE] \
-//        -o tools/micro/att_bench tools/micro/att_bench.cu
+// Stand-alone A/B driver of the tcgen05 patch-attention kernels (developer tool): the shipped kernel
+// (scenesplat_b200/csrc/attention_fwd.cu) against the round-1 kernel (tools/micro/attention_r1.cu) at a given shape,
+// with the largest output difference between the two.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -lineinfo \
+//        -o tools/micro/att_bench tools/micro/att_bench.cu scenesplat_b200/csrc/attention_fwd.cu
 //   att_bench n H d [reps] [order: 0 random | 1 identity]
 #include <cstdio>
 #include <cstdlib>
@@ -9,7 +10,7 @@
 #include <random>
 #include <algorithm>
 #include <numeric>
-#include "../../scenesplat_b200/csrc/attention_tc.cu"
+#include "attention_r1.cu"  // round-1 kernel (entry points renamed *_r1), kept for A/B; the shipped kernel is linked in
 namespace ss { unsigned long long g_launch_count = 0; }
 
 int main(int argc, char** argv) {
@@ -37,23 +38,43 @@ int main(int argc, char** argv) {
   cudaMemcpy(dtab, table.data(), table.size() * 4, cudaMemcpyHostToDevice);
   char* flush; cudaMalloc(&flush, 256 << 20);
   float scale = 1.f / sqrtf((float)d);
-  for (int i = 0; i < 2; ++i) {
-    int rc = ss_patch_attention(dq, dord, dtab, np, K, H, d, scale, dout, 0);
-    if (rc) { printf("launch rc=%d\n", rc); return 1; }
+  __nv_bfloat16* dout1; cudaMalloc(&dout1, (size_t)n * C * 2);
+  typedef int (*fn_t)(const void*, const int64_t*, const int32_t*, int, int, int, int, float, void*, void*);
+  struct { const char* name; fn_t fn; __nv_bfloat16* out; } impl[2] = {{"r1 (128-key steps, 1 S buffer/group)", ss_patch_attention_r1, dout1},
+                                                                      {"shipped (64-key steps, 2 S/P buffers/group)", ss_patch_attention, dout}};
+  const int only = argc > 6 ? atoi(argv[6]) : -1;  // 0: r1 only, 1: shipped only (for ncu)
+  for (int v = 0; v < 2; ++v) {
+    if (only >= 0 && only != v) continue;
+    for (int i = 0; i < 2; ++i) {
+      int rc = impl[v].fn(dq, dord, dtab, np, K, H, d, scale, impl[v].out, 0);
+      if (rc) { printf("launch rc=%d\n", rc); return 1; }
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float tot = 0;
+    for (int i = 0; i < reps; ++i) {
+      cudaMemsetAsync(flush, i, 256 << 20, 0);
+      cudaEventRecord(e0);
+      impl[v].fn(dq, dord, dtab, np, K, H, d, scale, impl[v].out, 0);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); tot += ms;
+    }
+    const double ms = tot / reps, exps = (double)n * K * H, flops = 4.0 * K * C * (double)n;
+    printf("n=%d H=%d d=%d order=%s %-44s: %.3f ms  %.1f TFLOP/s  %.2f Texp/s (MUFU peak 4.65)  %.0f GB/s io\n", n, H, d,
+           ident ? "identity" : "random", impl[v].name, ms, flops / ms / 1e9, exps / ms / 1e9, (double)n * C * 8 / ms / 1e6);
   }
-  if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  float tot = 0;
-  for (int i = 0; i < reps; ++i) {
-    cudaMemsetAsync(flush, i, 256 << 20, 0);
-    cudaEventRecord(e0);
-    ss_patch_attention(dq, dord, dtab, np, K, H, d, scale, dout, 0);
-    cudaEventRecord(e1); cudaEventSynchronize(e1);
-    float ms; cudaEventElapsedTime(&ms, e0, e1); tot += ms;
+  if (only < 0) {
+    std::vector<__nv_bfloat16> a((size_t)n * C), b((size_t)n * C);
+    cudaMemcpy(a.data(), dout1, a.size() * 2, cudaMemcpyDeviceToHost);
+    cudaMemcpy(b.data(), dout, b.size() * 2, cudaMemcpyDeviceToHost);
+    double mx = 0, sum = 0; size_t bad = 0;
+    for (size_t i = 0; i < a.size(); ++i) {
+      const float x = __bfloat162float(a[i]), y = __bfloat162float(b[i]);
+      if (!(fabsf(x - y) <= 1e30f)) ++bad;
+      mx = std::max(mx, (double)fabsf(x - y)); sum += fabs(x);
+    }
+    printf("  max |shipped - r1| = %.5f (mean |out| %.4f, non-finite differences: %zu)\n", mx, sum / a.size(), bad);
   }
-  const double ms = tot / reps, exps = (double)n * K * H, flops = 4.0 * K * C * (double)n;
-  printf("n=%d H=%d d=%d order=%s: %.3f ms  %.1f TFLOP/s  %.2f Texp/s (MUFU peak 4.65)  %.0f GB/s io\n", n, H, d,
-         ident ? "identity" : "random", ms, flops / ms / 1e9, exps / ms / 1e9, (double)n * C * 8 / ms / 1e6);
 #ifdef SS_ATT_TRACE
   {
     const int nb = np * H;

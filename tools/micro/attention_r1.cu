@@ -25,8 +25,8 @@
 // than 2^8 (any shift cancels in O / l; bf16 / fp32 have the exponent range), so O is touched by CUDA cores almost
 // only on the first chunk(s) of a tile.  The kernel is bound by the N*K*H exponentials, not by the tensor pipe
 // (see DESIGN.md); a fraction of them is evaluated on the FMA pipe (exp2_poly).
-#include "tc_common.cuh"
-#include "attention_math.cuh"
+#include "../../scenesplat_b200/csrc/tc_common.cuh"
+#include "../../scenesplat_b200/csrc/attention_math.cuh"
 #include "../../include/scenesplat_b200.h"
 
 #ifndef SS_ATT_WIDE
@@ -917,13 +917,13 @@ static int patch_attention_entry(const void* qkv_bf16, const int64_t* order_row,
   }
 }
 
-extern "C" int ss_patch_attention(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
+extern "C" int ss_patch_attention_r1(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
                                   int patch_size, int heads, int head_dim, float scale, void* out_bf16, void* stream_) {
   return patch_attention_entry(qkv_bf16, order_row, table, max_patches, patch_size, heads, head_dim, scale, out_bf16,
                                nullptr, 0, stream_);
 }
 
-extern "C" int ss_patch_attention_lse(const void* qkv_bf16, const int64_t* order_row, const int32_t* table,
+extern "C" int ss_patch_attention_lse_r1(const void* qkv_bf16, const int64_t* order_row, const int32_t* table,
                                       int max_patches, int patch_size, int heads, int head_dim, float scale,
                                       void* out_bf16, float* lse2, int64_t n, void* stream_) {
   if (!lse2 || n < 0) return SS_BAD_ARGS;

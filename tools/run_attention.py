@@ -1,9 +1,21 @@
 """Stand-alone driver of the tcgen05 patch-attention kernel at the dec0 / dec1 / enc0 shapes of the lang
-config (developer tool for timing and ncu captures)."""
-import os, sys, time
+config (developer tool for timing and ncu captures).
+
+  python tools/run_attention.py                   # own kernel at ATT_N / ATT_H / ATT_D (env), default dec0
+  python tools/run_attention.py --baseline flash  # + flash-attn 2.8.3 varlen with the reference's two row gathers
+                                                  #   (ptv3:188,208-216) on the same tensors, three shapes
+"""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from scenesplat_b200 import ops
+
+if "--baseline" in sys.argv and sys.argv[sys.argv.index("--baseline") + 1] == "flash":
+    import workloads as W
+    for r in W.attention_library_bar(torch.device("cuda")):
+        print(r)
+    sys.exit(0)
 
 n = int(os.environ.get("ATT_N", 299277))
 H = int(os.environ.get("ATT_H", 16))

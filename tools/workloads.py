@@ -343,7 +343,7 @@ def train_step(dev, rank, world, backbone_cfg, total_chunks=8, n_raw=180000, ste
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, float(loss)
+        return ms, float(loss.detach())
 
     ms, loss = timed(True)
     tot = torch.tensor([float(n_rank)], device=dev)
@@ -413,6 +413,9 @@ def sweep(dev, rank, world, model, text, sizes=(500000, 1000000, 2000000, 400000
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        _, st_cold = inference.sharded_chunk_labels(model, chunks, text, rank, world, "lpt", gather=False)
+        if world > 1:
+            dist.barrier()
         labels, st = inference.sharded_chunk_labels(model, chunks, text, rank, world, "lpt")
         ms_all = [st["ms"]]
         if world > 1:
@@ -426,7 +429,8 @@ def sweep(dev, rank, world, model, text, sizes=(500000, 1000000, 2000000, 400000
         row = dict(scene_gaussians=n_raw, room_edge_m=round(L, 1), chunks=len(chunks), chunk_voxels_min=min(vox),
                    chunk_voxels_max=max(vox), voxels_total=sum(vox), per_rank_ms=[round(m, 2) for m in ms_all],
                    per_rank_voxels=per_rank_vox, imbalance=max(per_rank_vox) / (sum(per_rank_vox) / world),
-                   voxels_per_s=sum(vox) / (slow * 1e-3), all_gather_ms=st.get("all_gather_ms"),
+                   voxels_per_s=sum(vox) / (slow * 1e-3), first_pass_ms_rank0=round(st_cold["ms"], 2),
+                   all_gather_ms=st.get("all_gather_ms"),
                    labels_complete=all(l is not None for l in labels))
         if cpu_rate:
             row["host_cpu_s_estimate"] = sum(vox) / cpu_rate
