@@ -23,6 +23,15 @@ __device__ __forceinline__ float exp2_poly(float x) {
   p = fmaf(p, f, 0.99992807355f);
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
 }
+// The same without the clamp, for arguments known to lie in [-126, 126].
+__device__ __forceinline__ float exp2_poly_bounded(float x) {
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05517166769f, 0.24261112209f);
+  p = fmaf(p, f, 0.69326098571f);
+  p = fmaf(p, f, 0.99992807355f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float y;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));

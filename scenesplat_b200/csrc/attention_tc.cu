@@ -1,0 +1,518 @@
+// Patch-wise serialized attention on the 5th-gen tensor cores (tcgen05 + TMEM), bf16 in / bf16 out.
+//
+// Replaces (reference): SerializedAttention.forward's `qkv[order]` gather, flash_attn_varlen_qkvpacked_func
+// and `feat[inverse]` gather (point_transformer_v3m1_base.py:181-216); patch rule of :114-170 comes in as
+// the device patch table (attention_simt.cu: patch_table_kernel).
+//
+// One CTA per (head, patch), 22 warps.  K and V of the head (<= 1024 tokens) stay resident in shared memory in the
+// UMMA no-swizzle core-matrix layout (K: K-major, V: MN-major).  They are gathered through the serialized order
+// with 16-byte cp.async by the 16 softmax warps themselves (one 64-key half chunk each, all in flight at once:
+// those warps have nothing else to do before the first S tile exists) behind per-chunk mbarriers.
+//
+// Single pass, online softmax, two query tiles of 128 rows in flight (one per softmax group), 128 keys per step:
+//   warps 0-15  softmax: group g = w / 8 (tiles g, g + 2, ..), column half = (w / 4) % 2 (64 of the step's keys),
+//               row quarter = w % 4 (one thread = one query row = one TMEM lane).  Four softmax warps per SM
+//               sub-partition keep the MUFU pipe fed while their neighbours sit in the TMEM / mbarrier part of a
+//               step.  The row max needs both halves: the two warps of a row exchange their local maxima through
+//               shared memory (double-buffered by step parity) behind a 64-thread named barrier and then take the
+//               same lazy-rescale decision.  Scores are read from TMEM twice (max sweep, exponential sweep) 32
+//               columns at a time, so a thread holds 32 scores and the kernel fits the 80 registers / thread that
+//               22 warps leave.  The two groups take turns in the exponential sweep (named barriers 9 / 10).
+//   warps 16-19 Q loaders (group, row half): the NEXT tile's rows are prefetched into registers and stored the
+//               moment the last Q K^T of the current tile has released the (single) Q buffer of the group
+//   warps 20,21 MMA issuers of group 0 / 1: S_g = Q_g K_c^T as soon as S_g of the previous step has been read into
+//               registers (s_free), O_g += P_g V_c and l_g += P_g 1 once P_g is written (p_ready)
+// TMEM columns: S_0 [0,128) S_1 [128,256) | P_0 [256,320) P_1 [320,384) (bf16 pairs) | O_0,l_0 [384,448) O_1,l_1
+// [448,512).  S and P are separate so the next Q K^T runs under the exponentials of the current step.
+// P is CUT to bf16 (no rounding instruction) and the row sum l is accumulated by the tensor core from the same
+// bf16 weights (P times a 16x16 tile of ones): O / l is an exactly normalised convex combination of V rows.
+// Online softmax with lazy rescaling: the running reference max only moves when the chunk max exceeds it by more
+// than 2^8 (any shift cancels in O / l; bf16 / fp32 have the exponent range), so O is touched by CUDA cores almost
+// only on the first chunk(s) of a tile.  The kernel is bound by the N*K*H exponentials, not by the tensor pipe
+// (see DESIGN.md); a fraction of them is evaluated on the FMA pipe (exp2_poly).
+//
+// Round 2 measured where a CTA's 134 k cycles go (clock64 traces, profiles/r2_attention.md: K/V gather prologue 20 k,
+// 64 steps of ~1250, tile epilogues 3.4 k each) and tried five restructurings on that evidence (64-key steps with
+// double-buffered S / P, a max-free softmax path under a Cauchy-Schwarz bound, pre-scaled keys, deeper TMEM prefetch,
+// L2 prefetch for the next CTA); none beat this kernel at head dim 48, see the profile notes and
+// tools/micro/attention_exp.cu.
+#include "tc_common.cuh"
+#include "attention_math.cuh"
+#include "../../include/scenesplat_b200.h"
+
+#ifndef SS_ATT_POLY
+#define SS_ATT_POLY 2
+#endif
+#ifndef SS_ATT_PP
+#define SS_ATT_PP 1
+#endif
+
+namespace ss {
+
+constexpr int kQB = 128;          // query rows per tile
+constexpr int kKC = 128;          // keys per chunk
+constexpr int kPCol = 256;        // first P column (bf16 pairs: 64 columns per tile)
+constexpr int kPStride = 64;
+constexpr int kOCol = 384;        // first O column
+constexpr int kOStride = 64;      // columns reserved per O tile (D of O, then the row-sum columns)
+constexpr float kLazy = 8.f;      // log2 units the running max may lag behind
+
+#ifdef SS_ATT_TRACE  // developer instrumentation (tools/micro/att_bench.cu): clock64 stamps per CTA
+constexpr int kTraceSlots = 176, kTraceCtas = 2048;
+__device__ long long g_att_trace[kTraceCtas * kTraceSlots];
+#define ATT_TRACE(slot)                                                                             \
+  do {                                                                                              \
+    if (lane == 0 && blockIdx.x < kTraceCtas) g_att_trace[blockIdx.x * kTraceSlots + (slot)] = clock64(); \
+  } while (0)
+#else
+#define ATT_TRACE(slot) do {} while (0)
+#endif
+
+template <int D, int KMAX>
+struct AttSmem {
+  static constexpr int kK = KMAX * D * 2;
+  static constexpr int kV = KMAX * D * 2;
+  static constexpr int kQ = kQB * D * 2;  // per buffer (one per softmax group)
+  static constexpr int kOffK = 0;
+  static constexpr int kOffV = kK;
+  static constexpr int kOffQ = kK + kV;
+  static constexpr int kOffBar = kOffQ + 2 * kQ;
+  static constexpr int kOffOnes = kOffBar + 256;  // 16 keys x 16 dims of bf16 1.0
+  static constexpr int kTotal = kOffOnes + 512 + 128;
+};
+
+constexpr int kAtt16Threads = 704;  // 16 softmax warps + 4 Q loader warps + 2 MMA warps
+
+template <int D, int KMAX>
+struct Att16Smem {
+  using B = AttSmem<D, KMAX>;
+  static constexpr int kOffXmax = B::kOffOnes + 512;  // [2 parities][2 groups][2 halves][128 rows] floats
+  static constexpr int kTotal = kOffXmax + 4096 + 128;
+};
+
+template <int D, int KMAX, int POLY>
+__global__ void __launch_bounds__(kAtt16Threads, 1)
+patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ order_row,
+                            const int4* __restrict__ table, int H, float scale_log2e, __nv_bfloat16* __restrict__ out,
+                            int pingpong, float* __restrict__ lse2, int64_t lse_stride) {
+  using S = AttSmem<D, KMAX>;
+  using S16 = Att16Smem<D, KMAX>;
+  const int4 e = table[blockIdx.x / H];
+  const int q_beg = e.x, n_q = e.y - e.x, kv_beg = e.z, kv_len = e.w - e.z;
+  if (n_q <= 0) return;  // block-uniform: unused table entry
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  uint64_t* bars = (uint64_t*)(smem + S::kOffBar);
+  uint64_t* kv_full = bars;       // [8]  64 lane arrivals (two half-chunk gathers)
+  uint64_t* q_full = bars + 8;    // [2]  64 lane arrivals (two row halves)
+  uint64_t* q_free = bars + 10;   // [2]
+  uint64_t* s_full = bars + 12;   // [2]
+  uint64_t* s_free = bars + 14;   // [2]  256 arrivals
+  uint64_t* p_ready = bars + 16;  // [2]  256 arrivals
+  uint64_t* pv_done = bars + 18;  // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 20);
+  float* xmax = (float*)(smem + S16::kOffXmax);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int h = blockIdx.x % H;
+  const int C = H * D;
+  const int nch = (kv_len + kKC - 1) / kKC;
+  const int nqb = (n_q + kQB - 1) / kQB;
+  constexpr int kChunksPerRow = D / 8;
+  constexpr int kItemsHalf = 2 * kChunksPerRow;  // 16-byte pieces per lane per 64 rows
+
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 8; ++c) tc::mbar_init(&kv_full[c], 64);
+    for (int g = 0; g < 2; ++g) {
+      tc::mbar_init(&q_full[g], 64);
+      tc::mbar_init(&q_free[g], 1);
+      tc::mbar_init(&s_full[g], 1);
+      tc::mbar_init(&s_free[g], 256);
+      tc::mbar_init(&p_ready[g], 256);
+      tc::mbar_init(&pv_done[g], 1);
+    }
+    tc::mbar_fence_init();
+  }
+  if (threadIdx.x >= 512 && threadIdx.x < 640) {
+    reinterpret_cast<uint32_t*>(smem + S::kOffOnes)[threadIdx.x - 512] = 0x3f803f80u;
+    tc::fence_proxy_async();
+  }
+  if (warp == 20) tc::tmem_alloc<512>(tmem_slot);
+
+  // gathers of 64 rows (same shared-memory layouts as the 8-warp kernel)
+  auto gather_kv_half = [&](int ch, int hh) {
+    const uint32_t sK = tc::smem_u32(smem + S::kOffK), sV = tc::smem_u32(smem + S::kOffV);
+#pragma unroll
+    for (int i0 = 0; i0 < kItemsHalf; i0 += 4) {
+      const __nv_bfloat16* src[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int item = lane + 32 * (i0 + u);
+        const int r = item / kChunksPerRow, c = item - r * kChunksPerRow;
+        const int j = ch * kKC + hh * 64 + r;
+        ok[u] = j < kv_len;
+        src[u] = qkv + (ok[u] ? (size_t)order_row[kv_beg + j] * (3 * C) : 0) + h * D + c * 8;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int item = lane + 32 * (i0 + u);
+        const int r = item / kChunksPerRow, c = item - r * kChunksPerRow;
+        const int j = ch * kKC + hh * 64 + r;
+        const uint32_t off = (uint32_t)(c * (KMAX * 16) + (j >> 3) * 128 + (j & 7) * 16);
+        tc::cp_async16(sK + off, src[u] + C, ok[u] ? 16u : 0u);
+        tc::cp_async16(sV + off, src[u] + 2 * C, ok[u] ? 16u : 0u);
+      }
+    }
+  };
+  auto gather_q_half = [&](int t, int hh) {
+    const uint32_t sQ = tc::smem_u32(smem + S::kOffQ + (t & 1) * S::kQ);
+#pragma unroll
+    for (int i0 = 0; i0 < kItemsHalf; i0 += 4) {
+      const __nv_bfloat16* src[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int item = lane + 32 * (i0 + u);
+        const int r = hh * 64 + item / kChunksPerRow, c = item % kChunksPerRow;
+        const int qi = t * kQB + r;
+        ok[u] = qi < n_q;
+        src[u] = qkv + (ok[u] ? (size_t)order_row[q_beg + qi] * (3 * C) : 0) + h * D + c * 8;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int item = lane + 32 * (i0 + u);
+        const int r = hh * 64 + item / kChunksPerRow, c = item % kChunksPerRow;
+        tc::cp_async16(sQ + (uint32_t)(c * (kQB * 16) + (r >> 3) * 128 + (r & 7) * 16), src[u], ok[u] ? 16u : 0u);
+      }
+    }
+  };
+  if (warp < 16 && (warp >> 1) < nch) gather_kv_half(warp >> 1, warp & 1);
+  if (warp >= 16 && warp < 20) {
+    const int g = (warp - 16) >> 1, hh = (warp - 16) & 1;
+    if (g < nqb) gather_q_half(g, hh);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 16) {
+    // =========================================================== softmax warps
+    if ((warp >> 1) < nch) {
+      tc::cp_async_wait_all();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&kv_full[warp >> 1]);
+    }
+    const int g = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t tS = t_lane + g * kKC + half * 64;
+    const uint32_t tP = t_lane + kPCol + g * kPStride + half * 32;
+    const uint32_t tO = t_lane + kOCol + g * kOStride;
+    const int pair_bar = 1 + g * 4 + quarter;  // named barrier of the two warps sharing these rows
+    const int ntiles = g == 0 ? (nqb + 1) / 2 : nqb / 2;
+    // ping-pong (named barriers 9 / 10, 256 waiting + 256 arriving threads): the groups take turns in the
+    // exponential sweep, so one group's MUFU burst overlaps the other group's TMEM / handshake part
+    const int total_other = (g == 0 ? nqb / 2 : (nqb + 1) / 2) * nch;
+    const bool pp = pingpong && nqb > 1;
+    if (pp && g == 1) asm volatile("bar.arrive 9, 512;" ::: "memory");  // group 0 takes the first turn
+    int s = 0;
+    for (int i = 0; i < ntiles; ++i) {
+      float msc = -INFINITY;
+      const int qi = (2 * i + g) * kQB + row;
+      const int64_t out_row = qi < n_q ? order_row[q_beg + qi] : -1;
+      for (int j = 0; j < nch; ++j, ++s) {
+        const int valid = kv_len - j * kKC - half * 64;  // valid keys among this warp's 64 columns (may be <= 0)
+        tc::mbar_wait(&s_full[g], s & 1);
+        tc::tc_fence_after();
+        [[maybe_unused]] const bool trw = (warp & 7) == 0 && s >= 8 && s < 16;
+        [[maybe_unused]] const int trb = 16 + g * 48 + (s - 8) * 6;
+        if (trw) ATT_TRACE(trb);
+        // ---- sweep 1: local row max over the warp's 64 columns
+        float mx = -INFINITY;
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          uint32_t v[32];
+          tc::tmem_ld32(tS + 32 * hq, v);
+          tc::tmem_ld_wait();
+          if (valid - 32 * hq < 32) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+              if (32 * hq + u >= valid) v[u] = 0xff800000u;
+          }
+          float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+          float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+#pragma unroll
+          for (int u = 6; u < 30; u += 4) {
+            m0 = fmax3(m0, __uint_as_float(v[u]), __uint_as_float(v[u + 1]));
+            m1 = fmax3(m1, __uint_as_float(v[u + 2]), __uint_as_float(v[u + 3]));
+          }
+          mx = fmaxf(mx, fmax3(m0, m1, fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]))));
+        }
+        if (trw) ATT_TRACE(trb + 1);
+        float* xm = xmax + ((s & 1) * 4 + g * 2) * 128;
+        xm[half * 128 + row] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mx = fmaxf(mx, xm[(half ^ 1) * 128 + row]);
+        if (trw) ATT_TRACE(trb + 2);
+        const float nm = mx * scale_log2e;  // scale > 0
+        const bool need = nm > msc + kLazy;
+        if (__any_sync(0xffffffffu, need)) {  // identical in both warps of the pair
+          const float newm = need ? nm : msc;
+          const float f = ex2_approx(msc - newm);
+          msc = newm;
+          if (j > 0 && half == 0) {
+            tc::mbar_wait(&pv_done[g], (s - 1) & 1);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int jo = 0; jo < D / 16 + 1; ++jo) {
+              uint32_t o[16];
+              tc::tmem_ld16(tO + jo * 16, o);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 16; ++u) o[u] = __float_as_uint(__uint_as_float(o[u]) * f);
+              tc::tmem_st16(tO + jo * 16, o);
+            }
+          }
+        }
+        if (j > 0) {  // P_g is read by the previous P V of the group until pv_done
+          tc::mbar_wait(&pv_done[g], (s - 1) & 1);
+          tc::tc_fence_after();
+        }
+        // ---- sweep 2: exponentials, 32 columns at a time
+        if (pp) {
+          if (g == 0) {
+            if (s <= total_other) asm volatile("bar.sync 9, 512;" ::: "memory");
+          } else {
+            asm volatile("bar.sync 10, 512;" ::: "memory");
+          }
+        }
+        if (trw) ATT_TRACE(trb + 3);
+        const float nmsc = -msc;
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          uint32_t v[32];
+          tc::tmem_ld32(tS + 32 * hq, v);
+          tc::tmem_ld_wait();
+          if (hq == 1) {  // S_g is in registers for the last time: the next Q K^T may overwrite it
+            tc::tc_fence_before();
+            tc::mbar_arrive(&s_free[g]);
+          }
+          if (valid - 32 * hq < 32) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+              if (32 * hq + u >= valid) v[u] = 0xff800000u;
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float x0 = fmaf(__uint_as_float(v[2 * u]), scale_log2e, nmsc);
+            const float x1 = fmaf(__uint_as_float(v[2 * u + 1]), scale_log2e, nmsc);
+            const float p0 = ((2 * u) & 7) < POLY ? exp2_poly(x0) : ex2_approx(x0);
+            const float p1 = ((2 * u + 1) & 7) < POLY ? exp2_poly(x1) : ex2_approx(x1);
+            pk[u] = tc::pack_bf16_bits(__float_as_uint(p0), __float_as_uint(p1));
+          }
+          tc::tmem_st16(tP + 16 * hq, pk);
+        }
+        if (trw) ATT_TRACE(trb + 4);
+        if (pp) {
+          if (g == 0) {
+            if (s < total_other) asm volatile("bar.arrive 10, 512;" ::: "memory");
+          } else {
+            if (s + 1 < total_other) asm volatile("bar.arrive 9, 512;" ::: "memory");
+          }
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&p_ready[g]);
+        if (trw) ATT_TRACE(trb + 5);
+      }
+      // ---- epilogue: this warp writes the column half [half * D/2, (half + 1) * D/2) of its rows
+      tc::mbar_wait(&pv_done[g], (s - 1) & 1);
+      tc::tc_fence_after();
+      const float lsum = __uint_as_float(tc::tmem_ld1(tO + D));
+      tc::tmem_ld_wait();
+      const float inv = 1.f / lsum;
+      if (lse2 && half == 0 && out_row >= 0) lse2[(size_t)h * lse_stride + q_beg + qi] = msc + log2f(lsum);
+      __nv_bfloat16* orow = out_row >= 0 ? out + (size_t)out_row * C + h * D + half * (D / 2) : nullptr;
+#pragma unroll
+      for (int jo = 0; jo < D / 16; ++jo) {
+        uint32_t o[8];
+        tc::tmem_ld8(tO + half * (D / 2) + jo * 8, o);
+        tc::tmem_ld_wait();
+        if (orow) {
+          uint4 o0;
+          o0.x = tc::pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+          o0.y = tc::pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+          o0.z = tc::pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+          o0.w = tc::pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+          *reinterpret_cast<uint4*>(orow + jo * 8) = o0;
+        }
+      }
+      tc::tc_fence_before();
+    }
+  } else if (warp < 20) {
+    // =========================================================== Q loaders: (group, row half)
+    const int g = (warp - 16) >> 1, hh = (warp - 16) & 1;
+    const int ntiles = g == 0 ? (nqb + 1) / 2 : nqb / 2;
+    if (ntiles > 0) {
+      tc::cp_async_wait_all();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&q_full[g]);
+    }
+    for (int i = 1; i < ntiles; ++i) {
+      const int t = 2 * i + g;
+      uint4 r[kItemsHalf];
+#pragma unroll
+      for (int u = 0; u < kItemsHalf; ++u) {
+        const int item = lane + 32 * u;
+        const int rr = hh * 64 + item / kChunksPerRow, c = item % kChunksPerRow;
+        const int qi = t * kQB + rr;
+        r[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (qi < n_q)
+          r[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)order_row[q_beg + qi] * (3 * C) + h * D + c * 8));
+      }
+      tc::mbar_wait_sleep(&q_free[g], (i - 1) & 1);
+      uint8_t* sQ = smem + S::kOffQ + g * S::kQ;
+#pragma unroll
+      for (int u = 0; u < kItemsHalf; ++u) {
+        const int item = lane + 32 * u;
+        const int rr = hh * 64 + item / kChunksPerRow, c = item % kChunksPerRow;
+        *reinterpret_cast<uint4*>(sQ + c * (kQB * 16) + (rr >> 3) * 128 + (rr & 7) * 16) = r[u];
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&q_full[g]);
+    }
+  } else {
+    // =========================================================== MMA issuers (warp 20: group 0, warp 21: group 1)
+    const int g = warp - 20;
+    const int total = (g == 0 ? (nqb + 1) / 2 : nqb / 2) * nch;
+    constexpr uint32_t idesc_s = tc::umma_idesc_bf16(kQB, kKC, 0, 0);
+    constexpr uint32_t idesc_o = tc::umma_idesc_bf16(kQB, D, 0, 1);
+    constexpr uint32_t idesc_l = tc::umma_idesc_bf16(kQB, 16, 0, 1);
+    const uint32_t sK = tc::smem_u32(smem + S::kOffK), sV = tc::smem_u32(smem + S::kOffV);
+    const uint32_t q0 = tc::smem_u32(smem + S::kOffQ + g * S::kQ) >> 4;
+    const uint32_t tSg = tmem_base + g * kKC;
+    const uint32_t tPg = tmem_base + kPCol + g * kPStride;
+    const uint32_t tOg = tmem_base + kOCol + g * kOStride;
+    const uint64_t dq_base = tc::umma_desc_nosw(0, kQB * 16, 128);
+    const uint64_t dk_base = tc::umma_desc_nosw(0, KMAX * 16, 128);
+    const uint64_t dv_base = tc::umma_desc_nosw(0, 128, KMAX * 16);
+    const uint64_t d_ones = tc::umma_desc_nosw(tc::smem_u32(smem + S::kOffOnes), 128, 256);
+    int kv_ready = 0, jn = 0, tn = 0;
+    auto issue_qk = [&]() {
+      const int j = jn;
+      if (j == 0) {
+        tc::mbar_wait(&q_full[g], tn & 1);
+        tc::tc_fence_after();
+      }
+      if (kv_ready <= j) {
+        tc::mbar_wait(&kv_full[j], 0);
+        tc::tc_fence_after();
+        kv_ready = j + 1;
+      }
+      const uint32_t k0 = (sK + j * (kKC / 8) * 128) >> 4;
+#pragma unroll
+      for (int t = 0; t < D / 16; ++t) {
+        const uint64_t da = dq_base | (uint64_t)((q0 + 2 * t * kQB) & 0x3fff);
+        const uint64_t db = dk_base | (uint64_t)((k0 + 2 * t * KMAX) & 0x3fff);
+        tc::umma_bf16_elect(tSg, da, db, idesc_s, t ? 1u : 0u);
+      }
+      tc::umma_commit_elect(&s_full[g]);
+      if (j == nch - 1) {
+        tc::umma_commit_elect(&q_free[g]);
+        jn = 0;
+        ++tn;
+      } else {
+        jn = j + 1;
+      }
+    };
+    if (total > 0) issue_qk();
+    int pc = 0;
+    for (int s = 0; s < total; ++s) {
+      const bool qk_first = s + 1 < total && jn != 0;
+      if (qk_first) {
+        tc::mbar_wait(&s_free[g], s & 1);
+        tc::tc_fence_after();
+        issue_qk();
+      }
+      tc::mbar_wait(&p_ready[g], s & 1);
+      tc::tc_fence_after();
+      const uint32_t v0 = (sV + pc * (kKC / 8) * 128) >> 4;
+#pragma unroll
+      for (int t = 0; t < kKC / 16; ++t) {
+        const uint64_t dv = dv_base | (uint64_t)((v0 + t * 16) & 0x3fff);
+        tc::umma_bf16_ts_elect(tOg, tPg + 8 * t, dv, idesc_o, (pc | t) ? 1u : 0u);
+      }
+#pragma unroll
+      for (int t = 0; t < kKC / 16; ++t)
+        tc::umma_bf16_ts_elect(tOg + D, tPg + 8 * t, d_ones, idesc_l, (pc | t) ? 1u : 0u);
+      tc::umma_commit_elect(&pv_done[g]);
+      pc = pc == nch - 1 ? 0 : pc + 1;
+      if (s + 1 < total && !qk_first) issue_qk();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 20) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int D, int POLY>
+static int launch_attention16(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches,
+                              int heads, float scale, void* out, float* lse2, int64_t lse_stride, cudaStream_t stream) {
+  constexpr int KMAX = 1024;
+  using S = Att16Smem<D, KMAX>;
+  auto kern = patch_attention_tc16_kernel<D, KMAX, POLY>;
+  SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+  dim3 grid((unsigned)((size_t)heads * max_patches));
+  constexpr int pp = SS_ATT_PP;
+  kern<<<grid, kAtt16Threads, S::kTotal, stream>>>((const __nv_bfloat16*)qkv, order_row, (const int4*)table, heads,
+                                                   scale * 1.4426950408889634f, (__nv_bfloat16*)out, pp, lse2, lse_stride);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+// SS_ATT_POLY (compile time): exponentials per 8 evaluated on the FMA pipe (2 and 3 tie at d = 48, 2 is 3 % faster at
+// d = 16 / 32); SS_ATT_PP: group ping-pong (1).  tools/micro/att_bench.cu builds this file with other values for A/B.
+template <int D>
+static int launch_attention(const void* qkv, const int64_t* order_row, const int32_t* table, int max_patches, int heads,
+                            float scale, void* out, float* lse2, int64_t lse_stride, cudaStream_t stream) {
+  return launch_attention16<D, SS_ATT_POLY>(qkv, order_row, table, max_patches, heads, scale, out, lse2, lse_stride, stream);
+}
+
+}  // namespace ss
+
+static int patch_attention_entry(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
+                                 int patch_size, int heads, int head_dim, float scale, void* out_bf16, float* lse2,
+                                 int64_t lse_stride, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (max_patches < 0 || heads < 1 || patch_size < 1 || patch_size > 1024 || !(scale > 0.f)) return SS_BAD_ARGS;
+  if (max_patches == 0) return SS_OK;
+  if ((long long)max_patches * heads > 0x7fffffffLL) return SS_BAD_ARGS;
+  if (!qkv_bf16 || !order_row || !table || !out_bf16) return SS_BAD_ARGS;
+  if (((uintptr_t)qkv_bf16 | (uintptr_t)out_bf16) % 16 != 0) return SS_BAD_ARGS;
+  switch (head_dim) {
+    case 16: return ss::launch_attention<16>(qkv_bf16, order_row, table, max_patches, heads, scale, out_bf16, lse2, lse_stride, stream);
+    case 32: return ss::launch_attention<32>(qkv_bf16, order_row, table, max_patches, heads, scale, out_bf16, lse2, lse_stride, stream);
+    case 48: return ss::launch_attention<48>(qkv_bf16, order_row, table, max_patches, heads, scale, out_bf16, lse2, lse_stride, stream);
+    default: return SS_BAD_ARGS;
+  }
+}
+
+extern "C" int ss_patch_attention(const void* qkv_bf16, const int64_t* order_row, const int32_t* table, int max_patches,
+                                  int patch_size, int heads, int head_dim, float scale, void* out_bf16, void* stream_) {
+  return patch_attention_entry(qkv_bf16, order_row, table, max_patches, patch_size, heads, head_dim, scale, out_bf16,
+                               nullptr, 0, stream_);
+}
+
+extern "C" int ss_patch_attention_lse(const void* qkv_bf16, const int64_t* order_row, const int32_t* table,
+                                      int max_patches, int patch_size, int heads, int head_dim, float scale,
+                                      void* out_bf16, float* lse2, int64_t n, void* stream_) {
+  if (!lse2 || n < 0) return SS_BAD_ARGS;
+  return patch_attention_entry(qkv_bf16, order_row, table, max_patches, patch_size, heads, head_dim, scale, out_bf16,
+                               lse2, n, stream_);
+}

@@ -224,7 +224,9 @@ class ChunkPipeline(object):
     def __init__(self, model, device=None):
         self.model = model
         self.device = device or next(model.parameters()).device
-        self.side = torch.cuda.Stream(device=self.device)
+        # high priority: the index phase is a handful of small kernels with host syncs between them; its CTAs must not
+        # queue behind the feature phase's waves or stage 1 stops hiding under stage 2
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
         self._keep = []  # prepared points stay referenced until the main stream has consumed them
 
     def _stage1(self, chunk):

@@ -1,8 +1,9 @@
 // Stand-alone A/B driver of the tcgen05 patch-attention kernels (developer tool): the shipped kernel
-// (scenesplat_b200/csrc/attention_fwd.cu) against the round-1 kernel (tools/micro/attention_r1.cu) at a given shape,
-// with the largest output difference between the two.
+// (scenesplat_b200/csrc/attention_tc.cu) against the round-2 experimental kernel (tools/micro/attention_exp.cu) at a
+// given shape, with the largest output difference between the two.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -lineinfo \
-//        -o tools/micro/att_bench tools/micro/att_bench.cu scenesplat_b200/csrc/attention_fwd.cu
+//        "-DSS_ATT_ENTRY(name)=name##_exp" [-DSS_ATT_TRACE2] -o tools/micro/att_bench tools/micro/att_bench.cu \
+//        scenesplat_b200/csrc/attention_tc.cu tools/micro/attention_exp.cu
 //   att_bench n H d [reps] [order: 0 random | 1 identity]
 #include <cstdio>
 #include <cstdlib>
@@ -10,8 +11,14 @@
 #include <random>
 #include <algorithm>
 #include <numeric>
-#include "attention_r1.cu"  // round-1 kernel (entry points renamed *_r1), kept for A/B; the shipped kernel is linked in
+#include "../../include/scenesplat_b200.h"
+#include <cuda_bf16.h>
+#include <cmath>
+extern "C" int ss_patch_attention_exp(const void*, const int64_t*, const int32_t*, int, int, int, int, float, void*, void*);
 namespace ss { unsigned long long g_launch_count = 0; }
+#ifdef SS_ATT_TRACE2
+extern "C" void ss_att_trace_read(long long* host, int* slots, int* ctas);
+#endif
 
 int main(int argc, char** argv) {
   const int n = argc > 1 ? atoi(argv[1]) : 299277, H = argc > 2 ? atoi(argv[2]) : 16, d = argc > 3 ? atoi(argv[3]) : 48;
@@ -40,9 +47,9 @@ int main(int argc, char** argv) {
   float scale = 1.f / sqrtf((float)d);
   __nv_bfloat16* dout1; cudaMalloc(&dout1, (size_t)n * C * 2);
   typedef int (*fn_t)(const void*, const int64_t*, const int32_t*, int, int, int, int, float, void*, void*);
-  struct { const char* name; fn_t fn; __nv_bfloat16* out; } impl[2] = {{"r1 (128-key steps, 1 S buffer/group)", ss_patch_attention_r1, dout1},
-                                                                      {"shipped (64-key steps, 2 S/P buffers/group)", ss_patch_attention, dout}};
-  const int only = argc > 6 ? atoi(argv[6]) : -1;  // 0: r1 only, 1: shipped only (for ncu)
+  struct { const char* name; fn_t fn; __nv_bfloat16* out; } impl[2] = {{"shipped (attention_tc.cu: 16 softmax warps, 128-key steps)", ss_patch_attention, dout1},
+                                                                      {"experimental (attention_exp.cu: 64-key steps, 2 S/P buffers)", ss_patch_attention_exp, dout}};
+  const int only = argc > 6 ? atoi(argv[6]) : -1;  // 0: shipped only, 1: experimental only (for ncu)
   for (int v = 0; v < 2; ++v) {
     if (only >= 0 && only != v) continue;
     for (int i = 0; i < 2; ++i) {
@@ -60,7 +67,7 @@ int main(int argc, char** argv) {
       float ms; cudaEventElapsedTime(&ms, e0, e1); tot += ms;
     }
     const double ms = tot / reps, exps = (double)n * K * H, flops = 4.0 * K * C * (double)n;
-    printf("n=%d H=%d d=%d order=%s %-44s: %.3f ms  %.1f TFLOP/s  %.2f Texp/s (MUFU peak 4.65)  %.0f GB/s io\n", n, H, d,
+    printf("n=%d H=%d d=%d order=%s %-62s: %.3f ms  %.1f TFLOP/s  %.2f Texp/s (MUFU peak 4.65)  %.0f GB/s io\n", n, H, d,
            ident ? "identity" : "random", impl[v].name, ms, flops / ms / 1e9, exps / ms / 1e9, (double)n * C * 8 / ms / 1e6);
   }
   if (only < 0) {
@@ -73,51 +80,35 @@ int main(int argc, char** argv) {
       if (!(fabsf(x - y) <= 1e30f)) ++bad;
       mx = std::max(mx, (double)fabsf(x - y)); sum += fabs(x);
     }
-    printf("  max |shipped - r1| = %.5f (mean |out| %.4f, non-finite differences: %zu)\n", mx, sum / a.size(), bad);
+    printf("  max |experimental - shipped| = %.5f (mean |out| %.4f, non-finite differences: %zu)\n", mx, sum / a.size(), bad);
   }
-#ifdef SS_ATT_TRACE
+#ifdef SS_ATT_TRACE2
   {
+    int kTraceSlots = 0, kTraceCtas = 0;
+    ss_att_trace_read(nullptr, &kTraceSlots, &kTraceCtas);
     const int nb = np * H;
-    std::vector<long long> tr((size_t)nb * ss::kTraceSlots);
-    cudaMemcpyFromSymbol(tr.data(), ss::g_att_trace, std::min(sizeof(long long) * tr.size(), sizeof(ss::g_att_trace)));
-    const int ncta = std::min<int>(nb, ss::kTraceCtas);
-    const char* names[16] = {"start", "loader_issued", "kv0", "kv1", "kv2", "kv3", "kv4", "kv5", "kv6", "kv7",
-                             "sm_first_S", "sm_pair0_end", "sm_all_end", "cta_end", "mma_end", "ld_q_done"};
+    const int ncta = std::min<int>(nb, kTraceCtas);
+    std::vector<long long> tr((size_t)kTraceCtas * kTraceSlots);
+    ss_att_trace_read(tr.data(), &kTraceSlots, &kTraceCtas);
     auto med = [&](int slot, int ref) {
       std::vector<long long> v;
-      for (int b = 0; b < ncta; ++b) {
-        long long t = tr[(size_t)b * ss::kTraceSlots + slot], t0 = tr[(size_t)b * ss::kTraceSlots + ref];
+      for (int b = 148; b < ncta; ++b) {  // skip the first wave (cold)
+        long long t = tr[(size_t)b * kTraceSlots + slot], t0 = tr[(size_t)b * kTraceSlots + ref];
         if (t && t0) v.push_back(t - t0);
       }
       if (v.empty()) return -1LL;
       std::sort(v.begin(), v.end());
       return v[v.size() / 2];
     };
-    if (getenv("ATT_TRACE_WIDE")) {  // 16-softmax-warp kernel: warps 0 (group 0) and 8 (group 1), steps 8..15
-      printf("  step |  g0: S_seen sweep1 exchanged exp_start exps_issued arrived |  g1: ...\n");
-      for (int st = 0; st < 8; ++st) {
-        printf("  %4d |", st + 8);
-        for (int g = 0; g < 2; ++g) { for (int k = 0; k < 6; ++k) printf(" %7lld", med(16 + g * 48 + st * 6 + k, 16)); printf(" |"); }
-        printf("\n");
-      }
-      return 0;
-    }
-    for (int s = 1; s < 16; ++s) printf("  %-14s median %8lld clk\n", names[s], med(s, 0));
-    printf("  tile transition of group 0 (relative to its last p_ready arrival of tile 0): q_free seen by loader %lld, Q landed %lld, "
-           "pv_done seen %lld, epilogue end %lld, q_full seen by MMA %lld, next S seen %lld\n",
-           med(115, 112), med(116, 112), med(113, 112), med(11, 112), med(114, 112), med(16, 112));
-    // second tile of each group (steady state): all relative to group 0's S-ready of step 8 (slot 16)
-    printf("  step |  g0: S_seen ld_done max_done arrived |  g1: S_seen ld_done max_done arrived | mma: p0_seen p0_issued p1_seen p1_issued\n");
-    for (int st = 0; st < 8; ++st) {
-      printf("  %4d |", st + 8);
-      for (int g = 0; g < 2; ++g) { for (int k = 0; k < 4; ++k) printf(" %7lld", med(16 + g * 32 + st * 4 + k, 16)); printf(" |"); }
-      for (int k = 0; k < 4; ++k) printf(" %7lld", med(80 + st * 4 + k, 16));
-      printf(" | sfree/qk g0 %7lld %7lld g1 %7lld %7lld", med(120 + st * 4, 16), med(121 + st * 4, 16), med(122 + st * 4, 16), med(123 + st * 4, 16));
-      printf("\n");
-    }
-    printf("  warp 0 step 10 (rel. to exp start): exps done %lld, pv_done passed %lld, STTM done %lld, arrived %lld\n", med(160, 163), med(161, 163), med(162, 163), med(152, 163));
-    printf("  group 0 step 10, warps 0..3: S_seen %lld %lld %lld %lld  arrived %lld %lld %lld %lld\n", med(156, 16), med(157, 16), med(158, 16),
-           med(159, 16), med(152, 16), med(153, 16), med(154, 16), med(155, 16));
+    const char* names[19] = {"entry", "after_first_sync", "kv0_landed", "kv1", "kv2", "kv3", "kv4", "kv5", "kv6", "kv7_landed",
+                             "first_qk_issued", "first_S_seen", "q_norm_done", "tile0_steps_done", "tile0_epilogue_done",
+                             "group0_done", "group1_done", "mma0_done", "cta_exit"};
+    for (int sl = 1; sl < 19; ++sl) printf("  %-20s median %8lld clk after entry\n", names[sl], med(sl, 0));
+    printf("  tile 1 of group 0, per step: S seen (rel. to step 0 of the tile) / p_ready arrived (rel. to own S seen)\n   ");
+    for (int j = 0; j < 16; ++j) printf(" %6lld", med(20 + j, 20));
+    printf("\n   ");
+    for (int j = 0; j < 16; ++j) printf(" %6lld", med(36 + j, 20 + j));
+    printf("\n");
   }
 #endif
   return 0;
