@@ -530,7 +530,9 @@ def main():
                         parallelism=f"chunk-sharded x{world} (no data-path collective)",
                         pipeline=("off" if args.no_pipeline else
                                   "index phase (+ H2D) of chunk i+1 on a side stream under the feature phase of chunk i"),
-                        l2="256 MiB flush buffer written before every step; activations (GBs) exceed L2 anyway"),
+                        l2="256 MiB flush buffer written before every step; activations (GBs) exceed L2 anyway",
+                        setup="a 40 GiB (+ 6 GiB per side stream) allocator reservation before the warm-up steps; no workload "
+                              "step runs outside warm-up + timed steps"),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=n_vox * 12,
                      ms_per_step=ms_e2e / args.steps, step_ms=e2e_stats,
                      api="ChunkPipeline(LangPretrainer(eval)) + zero_shot_labels(K=200) from pinned host inputs"),

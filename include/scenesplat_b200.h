@@ -147,6 +147,13 @@ int ss_subm_conv_gemm_pair(const void* in_bf16, const int32_t* pair_in, const vo
 int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float* bias, int64_t n, int k3, int cout,
                         void* out, int out_is_bf16, void* stream);
 
+/* The gather-sum fused with the Block's next two steps (point_transformer_v3m1_base.py:318-326, conv Linear folded into the
+ * taps): z = bias + sum_t prod[ypos[t][p], :] (fp32, never stored), res_out = res + LN(z; g0, b0) (fp32, may alias res),
+ * norm_out = LN(res_out; g1, b1) (bf16).  channels % 8 == 0, <= 1024. */
+int ss_subm_conv_reduce_add_ln(const void* prod_bf16, const int32_t* ypos, const float* bias, const float* res, const float* g0,
+                               const float* b0, const float* g1, const float* b1, float eps, int64_t n, int k3, int channels,
+                               float* res_out, void* norm_out_bf16, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * SerializedAttention (point_transformer_v3m1_base.py:114-222). */
 
@@ -187,6 +194,12 @@ int ss_patch_attention_backward(const void* qkv_bf16, const void* out_bf16, cons
  * NULL, act: 0 none, 1 exact GELU.  cin % 16 == 0, cout % 32 == 0. */
 int ss_linear_act_bf16(const void* x_bf16, const void* w_bf16, const float* bias, int64_t n, int cin, int cout, int act,
                        void* out_bf16, void* stream);
+
+/* The same GEMM with the residual add of a Block fused into the epilogue (point_transformer_v3m1_base.py:334-336,
+ * `point.feat = shortcut + drop_path(mlp(point.feat))` in eval): out_f32[n, cout] = res + (x W^T + b) in fp32 (res may be
+ * out_f32 itself: in place), and, if out_bf16 is not NULL, the bf16 copy of the result next to it. */
+int ss_linear_residual_bf16(const void* x_bf16, const void* w_bf16, const float* bias, const float* res, int64_t n, int cin,
+                            int cout, float* out_f32, void* out_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-wise fusions around the GEMMs of a Block (point_transformer_v3m1_base.py:318-338). */

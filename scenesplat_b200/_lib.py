@@ -36,10 +36,12 @@ SIGNATURES = {
     "ss_subm_conv_gemm256": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "ss_subm_conv_gemm_pair": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "ss_subm_conv_reduce": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp]),
+    "ss_subm_conv_reduce_add_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i64, _i, _i, _vp, _vp, _vp]),
     "ss_patch_table": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "ss_patch_attention_simt": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp]),
     "ss_patch_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "ss_linear_act_bf16": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
+    "ss_linear_residual_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "ss_stem_conv_wgrad_workspace_bytes": (_sz, [_i, _i]),
     "ss_stem_conv_wgrad": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ss_colsum_workspace_bytes": (_sz, [_i]),

@@ -243,6 +243,146 @@ conv_reduce_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __rest
   }
 }
 
+// The gather-sum fused with what follows the xCPE conv in a Block (point_transformer_v3m1_base.py:318-326 with the conv's
+// Linear folded into the taps): z = bias + sum_t prod[ypos[t][p], :] stays in registers (fp32, never rounded to bf16),
+// y = res + LN0(z) is written as the new fp32 residual stream and LN1(y) as the bf16 operand of the qkv GEMM.  One warp
+// per voxel, as in conv_reduce_kernel; the two LayerNorm reductions are warp shuffles.  Saves the write + read of z and
+// one launch per Block.
+template <int J>
+__global__ void __launch_bounds__(256)
+conv_reduce_add_ln_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __restrict__ ypos,
+                          const float* __restrict__ bias, const float* res, const float* __restrict__ g0,
+                          const float* __restrict__ b0, const float* __restrict__ g1, const float* __restrict__ b1, float eps,
+                          int64_t n, int k3, int C, float* res_out, __nv_bfloat16* __restrict__ norm_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float invC = 1.f / (float)C;
+  auto warp_sum = [](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  for (int64_t p = warp0; p < n; p += nwarp) {
+    float acc[J][8];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c0 = j * 256 + lane * 8;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[j][u] = (bias && c0 < C) ? bias[c0 + u] : 0.f;
+    }
+    for (int t0 = 0; t0 < k3; t0 += 32) {
+      const int32_t mypos = (t0 + lane < k3) ? ypos[(size_t)(t0 + lane) * n + p] : -1;
+      uint32_t m = __ballot_sync(0xffffffffu, mypos >= 0);
+      while (m) {
+        int32_t pos[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int t = m ? __ffs(m) - 1 : 0;
+          pos[q] = m ? __shfl_sync(0xffffffffu, mypos, t) : -1;
+          m &= m - 1;  // (0 stays 0)
+        }
+        uint4 v[4][J];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const int c0 = j * 256 + lane * 8;
+            v[q][j] = make_uint4(0u, 0u, 0u, 0u);
+            if (pos[q] >= 0 && c0 < C) v[q][j] = *reinterpret_cast<const uint4*>(prod + (size_t)pos[q] * C + c0);
+          }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (pos[q] < 0) continue;  // warp-uniform
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[q][j]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = __bfloat1622float2(h[u]);
+              acc[j][2 * u] += f.x;
+              acc[j][2 * u + 1] += f.y;
+            }
+          }
+        }
+      }
+    }
+    // ---- LN0(z)
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += acc[j][u];  // lanes past C hold zeros
+    float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const bool ok = j * 256 + lane * 8 < C;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float d = ok ? acc[j][u] - mean : 0.f;
+        q += d * d;
+      }
+    }
+    float rstd = rsqrtf(warp_sum(q) * invC + eps);
+    // ---- y = res + LN0(z)
+    s = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      if (c0 < C) {
+        const float4 ga = *reinterpret_cast<const float4*>(g0 + c0), gb = *reinterpret_cast<const float4*>(g0 + c0 + 4);
+        const float4 ba = *reinterpret_cast<const float4*>(b0 + c0), bb = *reinterpret_cast<const float4*>(b0 + c0 + 4);
+        const float4 xa = *reinterpret_cast<const float4*>(res + (size_t)p * C + c0);
+        const float4 xb = *reinterpret_cast<const float4*>(res + (size_t)p * C + c0 + 4);
+        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        const float xx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc[j][u] = xx[u] + ((acc[j][u] - mean) * rstd * gg[u] + bt[u]);
+          s += acc[j][u];
+        }
+        float4* o = reinterpret_cast<float4*>(res_out + (size_t)p * C + c0);
+        o[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        o[1] = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+      }
+    }
+    // ---- LN1(y) -> bf16
+    mean = warp_sum(s) * invC;
+    q = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const bool ok = j * 256 + lane * 8 < C;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float d = ok ? acc[j][u] - mean : 0.f;
+        q += d * d;
+      }
+    }
+    rstd = rsqrtf(warp_sum(q) * invC + eps);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      if (c0 < C) {
+        const float4 ga = *reinterpret_cast<const float4*>(g1 + c0), gb = *reinterpret_cast<const float4*>(g1 + c0 + 4);
+        const float4 ba = *reinterpret_cast<const float4*>(b1 + c0), bb = *reinterpret_cast<const float4*>(b1 + c0 + 4);
+        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = (acc[j][u] - mean) * rstd * gg[u] + bt[u];
+        uint4 w;
+        w.x = tc::pack_bf16(o[0], o[1]);
+        w.y = tc::pack_bf16(o[2], o[3]);
+        w.z = tc::pack_bf16(o[4], o[5]);
+        w.w = tc::pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(norm_out + (size_t)p * C + c0) = w;
+      }
+    }
+  }
+}
+
 template <int EPI>
 static int launch_head(const void* feat, const CUtensorMap& tmap, int64_t n, int channels, const HeadEpi& head,
                        cudaStream_t stream) {
@@ -299,6 +439,30 @@ int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float*
   else SS_RED_J_(float);
 #undef SS_RED_J_
 #undef SS_RED_
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+int ss_subm_conv_reduce_add_ln(const void* prod_bf16, const int32_t* ypos, const float* bias, const float* res,
+                               const float* g0, const float* b0, const float* g1, const float* b1, float eps, int64_t n, int k3,
+                               int channels, float* res_out, void* norm_out_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || k3 < 1 || channels < 8 || channels % 8 != 0 || channels > 1024) return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if (!prod_bf16 || !ypos || !res || !g0 || !b0 || !g1 || !b1 || !res_out || !norm_out_bf16) return SS_BAD_ARGS;
+  if (((uintptr_t)prod_bf16 | (uintptr_t)res | (uintptr_t)res_out | (uintptr_t)norm_out_bf16 | (uintptr_t)bias | (uintptr_t)g0 |
+       (uintptr_t)b0 | (uintptr_t)g1 | (uintptr_t)b1) % 16 != 0)
+    return SS_BAD_ARGS;
+  const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8), 32 * ss::kNumSMs);
+  const int j = (channels + 255) / 256;
+#define SS_RLN_(J)                                                                                                        \
+  ss::conv_reduce_add_ln_kernel<J><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)prod_bf16, ypos, bias, res, g0, b0, g1, b1, \
+                                                               eps, n, k3, channels, res_out, (__nv_bfloat16*)norm_out_bf16)
+  if (j == 1) SS_RLN_(1);
+  else if (j == 2) SS_RLN_(2);
+  else if (j == 3) SS_RLN_(3);
+  else SS_RLN_(4);
+#undef SS_RLN_
   SS_CHECK_LAUNCH();
   return SS_OK;
 }

@@ -1,8 +1,13 @@
 // Dense Linear layer on CTA PAIRS (tcgen05 cta_group::2): out = act(x W^T + b), bf16 in / bf16 out, fp32 accumulate.
 //
-// Replaces (reference): nn.Linear + nn.GELU of the MLP (point_transformer_v3m1_base.py:225-248, fc1 + act) as ONE kernel:
-// the activation is applied in the TMEM epilogue, so the N x 4C hidden tensor is written once instead of being written,
-// read and written again by a separate GELU pass.
+// Replaces (reference): every nn.Linear of the PTv3 forward (point_transformer_v3m1_base.py: qkv / proj :181-221, MLP
+// :225-248, pooling / unpooling projections :416,471-482) with the elementwise work that follows it fused into the TMEM
+// epilogue:
+//   ACT = 1  fc1 + bias + exact GELU: the N x 4C hidden tensor is written once instead of being written, read and
+//            written again by a separate GELU pass;
+//   RES = 1  fc2 + bias + residual add (Block, ref :334-336): the fp32 residual stream is updated in the epilogue and
+//            its bf16 shadow (the next Block's conv operand) is written beside it; the bf16 round trip of the MLP
+//            output and the separate add pass are gone.
 //
 // Why a CTA pair: with one CTA per tile, a 256 x 256 output tile needs both of its 128-row accumulators in that CTA's
 // TMEM (512 columns, conv_gemm2.cu), which leaves no second buffer, so the epilogue cannot overlap the next tile's MMAs
@@ -32,17 +37,19 @@ struct PairSmem {
   static constexpr int kA = 128 * kPBK * 2;
   static constexpr int kB = 128 * kPBK * 2;
   static constexpr int kStage = kA + kB;
-  static constexpr int kOffEpi = kPStages * kStage;  // 8 warps x 2 KB transpose buffers
-  static constexpr int kOffBar = kOffEpi + 8 * 2048;
+  static constexpr int kOffEpi = kPStages * kStage;  // 8 warps x (2 KB bf16 + 4 KB fp32) transpose buffers
+  static constexpr int kOffBar = kOffEpi + 8 * 6144;
   static constexpr int kTotal = kOffBar + 256 + 1024 /*alignment slack*/;
 };
 
 
-// ACT: 0 = none, 1 = exact GELU
-template <int ACT>
+// ACT: 0 = none, 1 = exact GELU.  RES: 1 = out_f32 = res + (x W^T + b) (res may be out_f32 itself), bf16 copy in `out`
+// (optional).
+template <int ACT, int RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
 linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                   const float* __restrict__ bias, int64_t n_rows, int cin, int cout, __nv_bfloat16* __restrict__ out) {
+                   const float* __restrict__ bias, int64_t n_rows, int cin, int cout, __nv_bfloat16* __restrict__ out,
+                   const float* res, float* out_f32) {
   using S = PairSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -128,7 +135,10 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 0..7: (row quarter, column half)
-    uint8_t* stg = smem + S::kOffEpi + warp * 2048;  // [32 rows][64 B], 16-byte chunks XOR-swizzled by (row >> 1) & 3
+    // bf16 tile [32 rows][64 B], 16-byte chunks XOR-swizzled by (row >> 1) & 3; RES: fp32 tile [32 rows][128 B] behind it,
+    // 16-byte chunks XOR-swizzled by row & 7
+    uint8_t* stg = smem + S::kOffEpi + warp * 6144;
+    uint8_t* stf = stg + 2048;
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int it = 0;
@@ -145,6 +155,49 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         if (c0 >= cout) break;
         uint32_t v[32];
         tc::tmem_ld32(t_lane + b * kPTileN + half * 128 + j * 32, v);
+        if constexpr (RES == 1) {
+          // residual tile -> shared memory with coalesced 128-byte row segments (8 lanes per row, 4 rows per access)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3), cc = lane & 7;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < n_rows) x = *reinterpret_cast<const float4*>(res + (size_t)(row0 + r) * cout + c0 + cc * 4);
+            *reinterpret_cast<float4*>(stf + r * 128 + ((cc ^ (r & 7)) << 4)) = x;
+          }
+          __syncwarp();
+          tc::tmem_ld_wait();
+          // this thread's row: accumulator + bias + residual -> fp32 tile (in place) and bf16 tile
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float y[8];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              const int cc = 2 * u + hlf;
+              float4* ptr = reinterpret_cast<float4*>(stf + lane * 128 + ((cc ^ (lane & 7)) << 4));
+              const float4 x = *ptr;
+              float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bias) bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + cc * 4));
+              y[hlf * 4 + 0] = x.x + (__uint_as_float(v[cc * 4 + 0]) + bb.x);
+              y[hlf * 4 + 1] = x.y + (__uint_as_float(v[cc * 4 + 1]) + bb.y);
+              y[hlf * 4 + 2] = x.z + (__uint_as_float(v[cc * 4 + 2]) + bb.z);
+              y[hlf * 4 + 3] = x.w + (__uint_as_float(v[cc * 4 + 3]) + bb.w);
+              *ptr = make_float4(y[hlf * 4 + 0], y[hlf * 4 + 1], y[hlf * 4 + 2], y[hlf * 4 + 3]);
+            }
+            uint4 o;
+            o.x = tc::pack_bf16(y[0], y[1]);
+            o.y = tc::pack_bf16(y[2], y[3]);
+            o.z = tc::pack_bf16(y[4], y[5]);
+            o.w = tc::pack_bf16(y[6], y[7]);
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = o;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3), cc = lane & 7;
+            const float4 y = *reinterpret_cast<const float4*>(stf + r * 128 + ((cc ^ (r & 7)) << 4));
+            if (row0 + r < n_rows) *reinterpret_cast<float4*>(out_f32 + (size_t)(row0 + r) * cout + c0 + cc * 4) = y;
+          }
+        } else {
         tc::tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -168,13 +221,16 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           o.w = tc::pack_bf16(f[6], f[7]);
           *reinterpret_cast<uint4*>(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = o;
         }
+        }
         __syncwarp();
+        if (RES == 0 || out != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = i * 8 + (lane >> 2), cc = lane & 3;
-          const uint4 o = *reinterpret_cast<const uint4*>(stg + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4));
-          if (row0 + r < n_rows)
-            *reinterpret_cast<uint4*>(out + (size_t)(row0 + r) * cout + c0 + cc * 8) = o;  // 4 lanes = 64 contiguous bytes
+          for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + (lane >> 2), cc = lane & 3;
+            const uint4 o = *reinterpret_cast<const uint4*>(stg + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4));
+            if (row0 + r < n_rows)
+              *reinterpret_cast<uint4*>(out + (size_t)(row0 + r) * cout + c0 + cc * 8) = o;  // 4 lanes = 64 contiguous bytes
+          }
         }
         __syncwarp();
       }
@@ -192,32 +248,46 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   }
 }
 
-template <int ACT>
+template <int ACT, int RES>
 static int launch_linear_pair(const CUtensorMap& tx, const CUtensorMap& tw, const float* bias, int64_t n, int cin, int cout,
-                              void* out, cudaStream_t stream) {
-  auto kern = linear_pair_kernel<ACT>;
+                              void* out, const float* res, float* out_f32, cudaStream_t stream) {
+  auto kern = linear_pair_kernel<ACT, RES>;
   SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::kTotal));
   const int64_t n_items = ((n + kPTileM - 1) / kPTileM) * ((cout + kPTileN - 1) / kPTileN);
   const int pairs = (int)imin64(n_items, kNumSMs / 2);
-  kern<<<2 * pairs, kPThreads, PairSmem::kTotal, stream>>>(tx, tw, bias, n, cin, cout, (__nv_bfloat16*)out);
+  kern<<<2 * pairs, kPThreads, PairSmem::kTotal, stream>>>(tx, tw, bias, n, cin, cout, (__nv_bfloat16*)out, res, out_f32);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
 
 }  // namespace ss
 
-extern "C" int ss_linear_act_bf16(const void* x_bf16, const void* w_bf16, const float* bias, int64_t n, int cin, int cout,
-                                  int act, void* out_bf16, void* stream_) {
+static int linear_pair_entry(const void* x_bf16, const void* w_bf16, const float* bias, int64_t n, int cin, int cout, int act,
+                             void* out_bf16, const float* res, float* out_f32, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n < 0 || cin < 16 || cin % 16 != 0 || cout < 32 || cout % 32 != 0 || act < 0 || act > 1) return SS_BAD_ARGS;
   if (n == 0) return SS_OK;
-  if (!x_bf16 || !w_bf16 || !out_bf16) return SS_BAD_ARGS;
-  if (((uintptr_t)x_bf16 | (uintptr_t)w_bf16 | (uintptr_t)out_bf16 | (uintptr_t)bias) % 16 != 0) return SS_BAD_ARGS;
+  if (!x_bf16 || !w_bf16) return SS_BAD_ARGS;
+  if (((uintptr_t)x_bf16 | (uintptr_t)w_bf16 | (uintptr_t)out_bf16 | (uintptr_t)bias | (uintptr_t)res | (uintptr_t)out_f32) % 16 != 0)
+    return SS_BAD_ARGS;
   CUtensorMap tx, tw;
   int rc = ss::make_tmap_bf16_2d(&tx, x_bf16, (uint64_t)n, (uint64_t)cin, 128, ss::kPBK);
   if (rc) return rc;
   rc = ss::make_tmap_bf16_2d(&tw, w_bf16, (uint64_t)cout, (uint64_t)cin, 128, ss::kPBK);
   if (rc) return rc;
-  return act == 1 ? ss::launch_linear_pair<1>(tx, tw, bias, n, cin, cout, out_bf16, stream)
-                  : ss::launch_linear_pair<0>(tx, tw, bias, n, cin, cout, out_bf16, stream);
+  if (res) return ss::launch_linear_pair<0, 1>(tx, tw, bias, n, cin, cout, out_bf16, res, out_f32, stream);
+  return act == 1 ? ss::launch_linear_pair<1, 0>(tx, tw, bias, n, cin, cout, out_bf16, nullptr, nullptr, stream)
+                  : ss::launch_linear_pair<0, 0>(tx, tw, bias, n, cin, cout, out_bf16, nullptr, nullptr, stream);
+}
+
+extern "C" int ss_linear_act_bf16(const void* x_bf16, const void* w_bf16, const float* bias, int64_t n, int cin, int cout,
+                                  int act, void* out_bf16, void* stream_) {
+  if (!out_bf16) return SS_BAD_ARGS;
+  return linear_pair_entry(x_bf16, w_bf16, bias, n, cin, cout, act, out_bf16, nullptr, nullptr, stream_);
+}
+
+extern "C" int ss_linear_residual_bf16(const void* x_bf16, const void* w_bf16, const float* bias, const float* res, int64_t n,
+                                       int cin, int cout, float* out_f32, void* out_bf16, void* stream_) {
+  if (!res || !out_f32) return SS_BAD_ARGS;
+  return linear_pair_entry(x_bf16, w_bf16, bias, n, cin, cout, 0, out_bf16, res, out_f32, stream_);
 }

@@ -239,10 +239,8 @@ def subm_conv_simt(x, nbr, wt, bias=None, scale=None, shift=None, act=0, out_dty
     return out
 
 
-def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16, impl="auto"):
-    """tcgen05 gather-GEMM (+ gather-sum).  w_bf16: [k^3, cout, cin] bf16.  impl: "auto" = CTA pairs for cout >= 256
-    (csrc/conv_gemm3.cu), the single-CTA two-accumulator kernel below that (csrc/conv_gemm2.cu); "single" / "pair"
-    force one of them (they are bit-identical; tests compare them)."""
+def _subm_conv_products(x_bf16, pairs, w_bf16, impl="auto"):
+    """Stage 1 of the tensor-core conv: prod[r, :] = x[pair_in[r], :] @ w[tap(r)]^T (bf16 [p_pad, cout])."""
     k3, cout, cin = w_bf16.shape
     p_pad = pairs["p_pad"]
     if pairs.get("tile") != CONV_TILE:
@@ -250,13 +248,40 @@ def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16
     prod = torch.empty((max(p_pad, 1), cout), dtype=_BF16, device=x_bf16.device)
     pair = cout >= 256 if impl == "auto" else impl == "pair"
     fn = "ss_subm_conv_gemm_pair" if pair else "ss_subm_conv_gemm256"
-    L.call(fn, L.ptr(x_bf16.contiguous()), L.ptr(pairs["pair_in"]), L.ptr(w_bf16),
+    x_bf16 = x_bf16.contiguous()
+    L.call(fn, L.ptr(x_bf16), L.ptr(pairs["pair_in"]), L.ptr(w_bf16),
            L.ptr(pairs["tile_tap"]), p_pad, k3, cin, cout, L.ptr(prod), L.stream(),
            meta=dict(flops=2.0 * pairs["pairs"] * cin * cout, bytes=2.0 * pairs["pairs"] * (cin + cout)))
+    return prod
+
+
+def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16, impl="auto"):
+    """tcgen05 gather-GEMM (+ gather-sum).  w_bf16: [k^3, cout, cin] bf16.  impl: "auto" = CTA pairs for cout >= 256
+    (csrc/conv_gemm3.cu), the single-CTA two-accumulator kernel below that (csrc/conv_gemm2.cu); "single" / "pair"
+    force one of them (they are bit-identical; tests compare them)."""
+    k3, cout, cin = w_bf16.shape
+    prod = _subm_conv_products(x_bf16, pairs, w_bf16, impl)
     out = torch.empty((n, cout), dtype=out_dtype, device=x_bf16.device)
     L.call("ss_subm_conv_reduce", L.ptr(prod), L.ptr(pairs["ypos"]), L.ptr(bias), n, k3, cout, L.ptr(out), _isbf(out),
            L.stream(), meta=dict(bytes=2.0 * pairs["pairs"] * cout + n * (4.0 * k3 + out.element_size() * cout)))
     return out
+
+
+def subm_conv_gemm_add_ln(x_bf16, pairs, w_bf16, bias, res_f32, ln0, ln1, eps=1e-5, inplace=True):
+    """The conv with the Block's next two steps fused into its gather-sum stage: y = res + LN0(conv(x)) (fp32, `res`
+    itself when inplace) and LN1(y) (bf16).  The conv output never reaches memory.  -> (y, LN1(y))."""
+    k3, cout, cin = w_bf16.shape
+    n = res_f32.shape[0]
+    if res_f32.dtype != torch.float32 or not res_f32.is_contiguous() or tuple(res_f32.shape) != (n, cout):
+        raise L.CudaKernelError("subm_conv_gemm_add_ln: the residual must be a contiguous fp32 [n, cout] tensor")
+    prod = _subm_conv_products(x_bf16, pairs, w_bf16)
+    out = res_f32 if inplace else torch.empty_like(res_f32)
+    norm = torch.empty((n, cout), dtype=_BF16, device=x_bf16.device)
+    (g0, b0), (g1, b1) = ln0, ln1
+    L.call("ss_subm_conv_reduce_add_ln", L.ptr(prod), L.ptr(pairs["ypos"]), L.ptr(bias), L.ptr(res_f32), L.ptr(g0), L.ptr(b0),
+           L.ptr(g1), L.ptr(b1), float(eps), n, k3, cout, L.ptr(out), L.ptr(norm), L.stream(),
+           meta=dict(bytes=2.0 * pairs["pairs"] * cout + n * (4.0 * k3 + 10.0 * cout)))
+    return out, norm
 
 
 # ------------------------------------------------------------------------------------------- attention
@@ -333,6 +358,26 @@ def linear_act(x_bf16, w_bf16, bias_f32=None, act=0):
     L.call("ss_linear_act_bf16", L.ptr(x_bf16), L.ptr(w_bf16), L.ptr(bias_f32), n, cin, cout, int(act), L.ptr(out), L.stream(),
            meta=dict(flops=2.0 * n * cin * cout, bytes=2.0 * (n * cin + n * cout + cin * cout)))
     return out
+
+
+def linear_ok(cin: int, cout: int) -> bool:
+    """Shapes the CTA-pair GEMM tiles (K in 16-element steps, output columns in 32-column groups)."""
+    return cin >= 16 and cin % 16 == 0 and cout >= 32 and cout % 32 == 0
+
+
+def linear_residual(x_bf16, w_bf16, bias_f32, res_f32, want_bf16=True, inplace=True):
+    """res + (x W^T + b) with the add in the GEMM epilogue: -> (fp32 [n, cout] (res itself when inplace), bf16 copy or None)."""
+    x_bf16, w_bf16 = x_bf16.contiguous(), w_bf16.contiguous()
+    n, cin = x_bf16.shape
+    cout = w_bf16.shape[0]
+    if res_f32.dtype != torch.float32 or not res_f32.is_contiguous() or tuple(res_f32.shape) != (n, cout):
+        raise L.CudaKernelError("linear_residual: the residual must be a contiguous fp32 [n, cout] tensor")
+    out = res_f32 if inplace else torch.empty_like(res_f32)
+    shadow = torch.empty((n, cout), dtype=_BF16, device=x_bf16.device) if want_bf16 else None
+    L.call("ss_linear_residual_bf16", L.ptr(x_bf16), L.ptr(w_bf16), L.ptr(bias_f32), L.ptr(res_f32), n, cin, cout, L.ptr(out),
+           L.ptr(shadow), L.stream(),
+           meta=dict(flops=2.0 * n * cin * cout, bytes=2.0 * (n * cin + cin * cout) + n * cout * (8.0 + (2.0 if want_bf16 else 0.0))))
+    return out, shadow
 
 
 # ------------------------------------------------------------------------------------------- row-wise fusions

@@ -84,21 +84,24 @@ class _Cache:
 _cache = _Cache()
 
 
-def linear_bf16(lin: nn.Linear, x):
-    """Library GEMM (cuBLASLt) in bf16, fp32 accumulate."""
-    w, b = _cache.get(lin, "lin", [lin.weight] + ([lin.bias] if lin.bias is not None else []),
+def linear_params(lin: nn.Linear):
+    """(bf16 weight [cout, cin], fp32 bias or None) of a Linear, cached on the module."""
+    return _cache.get(lin, "lin", [lin.weight] + ([lin.bias] if lin.bias is not None else []),
                       lambda: (lin.weight.detach().to(BF16).contiguous(),
-                               lin.bias.detach().to(BF16).contiguous() if lin.bias is not None else None))
+                               lin.bias.detach().float().clone() if lin.bias is not None else None))
+
+
+def linear_bf16(lin: nn.Linear, x, act=0):
+    """nn.Linear (+ exact GELU when act = 1) on bf16 operands with fp32 accumulation: the package's tcgen05 CTA-pair GEMM
+    (csrc/gemm2cta.cu) with bias / activation in the epilogue.  Channel counts outside its tiling (K not a multiple of
+    16, output columns not a multiple of 32: none in the PTv3 configs) go to the library GEMM."""
+    w, b = linear_params(lin)
     if x.dtype != BF16:
         x = x.to(BF16)
-    if L.PROFILE is None or L.PROFILE_ONLY is not None:
-        return F.linear(x, w, b)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    y = F.linear(x, w, b)
-    e1.record()
-    L.PROFILE.setdefault("torch.linear(cuBLASLt)", []).append((e0, e1, dict(flops=2.0 * x.shape[0] * w.shape[0] * w.shape[1])))
-    return y
+    if x.is_cuda and ops.linear_ok(lin.in_features, lin.out_features):
+        return ops.linear_act(x, w, b, act=act)
+    y = F.linear(x, w, b.to(BF16) if b is not None else None)
+    return ops.affine_act(y, act=1) if act else y
 
 
 def cpe_folded(conv, lin: nn.Linear):
@@ -249,19 +252,25 @@ class MLP(nn.Module):
         self.fc2 = nn.Linear(hidden_channels, out_channels)
         self.drop = nn.Dropout(drop)
 
+    def _exact_gelu(self):
+        return isinstance(self.act, nn.GELU) and self.act.approximate == "none"
+
     def forward(self, x):
-        fc1 = self.fc1
-        exact_gelu = isinstance(self.act, nn.GELU) and self.act.approximate == "none"
-        if exact_gelu and x.is_cuda and fc1.in_features % 16 == 0 and fc1.out_features % 32 == 0:
-            # fc1 + bias + GELU as ONE kernel on CTA pairs (csrc/gemm2cta.cu): the N x 4C hidden is written once
-            w, b = _cache.get(fc1, "lin_act", [fc1.weight] + ([fc1.bias] if fc1.bias is not None else []),
-                              lambda: (fc1.weight.detach().to(BF16).contiguous(),
-                                       fc1.bias.detach().float().clone() if fc1.bias is not None else None))
-            h = ops.linear_act(x if x.dtype == BF16 else x.to(BF16), w, b, act=1)
+        # fc1 + bias + GELU is ONE kernel (the N x 4C hidden is written once), fc2 + bias another
+        if self._exact_gelu():
+            h = linear_bf16(self.fc1, x, act=1)
         else:
-            h = linear_bf16(fc1, x)
-            h = ops.affine_act(h, act=1) if exact_gelu else self.act(h)
+            h = self.act(linear_bf16(self.fc1, x))
         return linear_bf16(self.fc2, h)
+
+    def forward_residual(self, x, res):
+        """res + MLP(x) with the residual add in fc2's epilogue (eval, DropPath = identity): -> (fp32 residual stream,
+        updated in place, and its bf16 copy), or None when the shapes are outside the fused kernel."""
+        if not (self._exact_gelu() and x.is_cuda and ops.linear_ok(self.fc2.in_features, self.fc2.out_features)):
+            return None
+        h = linear_bf16(self.fc1, x, act=1)
+        w, b = linear_params(self.fc2)
+        return ops.linear_residual(h, w, b, res)
 
 
 class Block(PointModule):
@@ -301,15 +310,24 @@ class Block(PointModule):
         if conv.tensor_core_ok() and cpe_lin.out_features % 32 == 0:
             w_fold, b_fold = cpe_folded(conv, cpe_lin)  # conv and Linear composed into one tensor-core conv
             ent = spconv.kernel_map_for(point, conv.kernel_size, want_pairs=True)
-            z = ops.subm_conv_gemm(_bf16_of(point, src), ent["pairs"], w_fold, b_fold, x.shape[0], out_dtype=BF16)
+            if self.channels >= 128 and cpe_ln.eps == self.norm1[0].eps:
+                # gather-sum + LN(cpe) + residual add + LN(norm1) in one pass: the conv output stays in registers
+                x, h = ops.subm_conv_gemm_add_ln(_bf16_of(point, src), ent["pairs"], w_fold, b_fold, x.contiguous(),
+                                                 ln_params(cpe_ln), ln_params(self.norm1[0]), cpe_ln.eps, inplace=False)
+                z = None
+            else:
+                z = ops.subm_conv_gemm(_bf16_of(point, src), ent["pairs"], w_fold, b_fold, x.shape[0], out_dtype=BF16)
         else:
             y = conv.conv_point(point, _bf16_of(point, src))
             z = linear_bf16(cpe_lin, y)
-        x, h = ops.add_layernorm(x, z, ln_params(cpe_ln), ln_params(self.norm1[0]), cpe_ln.eps, norm_dtype=BF16)
+        if z is not None:
+            x, h = ops.add_layernorm(x, z, ln_params(cpe_ln), ln_params(self.norm1[0]), cpe_ln.eps, norm_dtype=BF16)
         qkv = linear_bf16(self.attn.qkv, h)
         a = self.attn.core(point, qkv)
         p = linear_bf16(self.attn.proj, a)
         x, h = ops.add_layernorm(x, p, None, ln_params(self.norm2[0]), self.norm2[0].eps, norm_dtype=BF16, inplace=True)
+        # (MLP.forward_residual -- fc2 with the residual add in its epilogue -- is built and tested but measured SLOWER
+        # than GEMM + this add pass at every Block shape: 1.43 vs 1.37 ms at dec0, profiles/r2_gemm.md)
         m = self.mlp[0](h)
         x, xb = ops.add_layernorm(x, m, None, None, norm_dtype=BF16, inplace=True)
         point.feat = x

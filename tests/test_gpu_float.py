@@ -182,6 +182,35 @@ def test_lang_head_and_losses_golden(golden):
     np.testing.assert_allclose(con.numpy(), g["con"], rtol=1e-4)
 
 
+@pytest.mark.parametrize("c", [128, 256, 512, 768])
+def test_subm_conv_fused_add_layernorm(c):
+    """conv gather-sum + LN + residual add + LN in one kernel (ss_subm_conv_reduce_add_ln) against the two-kernel path
+    (ss_subm_conv_reduce -> fp32, then ss_add_layernorm): same products, same summation order; the only difference is
+    the order of the LayerNorm reductions (warp shuffles vs. sub-group sums): 1e-5 relative."""
+    from scenesplat_b200 import ops
+    g, batch, offset, code, order, inv, depth = _scene(5000)
+    torch.manual_seed(2)
+    n = g.shape[0]
+    x = torch.randn(n, c).bfloat16().cuda()
+    w = (torch.randn(27, c, c) * (1.0 / (c * 7) ** 0.5)).bfloat16().cuda()
+    b = torch.randn(c).cuda()
+    res = (torch.randn(n, c) * 2).cuda()
+    ln0 = (torch.rand(c).cuda() + 0.5, torch.randn(c).cuda())
+    ln1 = (torch.rand(c).cuda() + 0.5, torch.randn(c).cuda())
+    nbr, cnt = ops.kmap_build(dev(g), dev(batch), dev(code[0]), dev(order[0]), depth, 0, 3)
+    pairs = ops.kmap_pairs(nbr, dev(order[0]), 3, cnt.cpu().numpy())
+    z = ops.subm_conv_gemm(x, pairs, w, b, n, out_dtype=torch.float32)
+    want_y, want_h = ops.add_layernorm(res, z, ln0, ln1, 1e-5, norm_dtype=torch.float32)
+    got_y, got_h = ops.subm_conv_gemm_add_ln(x, pairs, w, b, res, ln0, ln1, 1e-5, inplace=False)
+    np.testing.assert_allclose(got_y.cpu().numpy(), want_y.cpu().numpy(), rtol=2e-5, atol=2e-5)
+    # bf16 output: equal up to one rounding step of the fp32 value it was rounded from
+    np.testing.assert_allclose(got_h.float().cpu().numpy(), want_h.cpu().numpy(), rtol=2.0 ** -7, atol=1e-3)
+    # in place
+    r2 = res.clone()
+    y2, h2 = ops.subm_conv_gemm_add_ln(x, pairs, w, b, r2, ln0, ln1, 1e-5, inplace=True)
+    assert y2.data_ptr() == r2.data_ptr() and torch.equal(y2, got_y) and torch.equal(h2, got_h)
+
+
 @pytest.mark.parametrize("logits", ["moderate", "huge", "hot_keys", "hot_rows"])
 @pytest.mark.parametrize("H,d,K", [(2, 16, 1024), (3, 32, 1024), (2, 48, 1024), (4, 16, 256), (1, 48, 100)])
 def test_patch_attention_tensor_core(H, d, K, logits):
@@ -226,6 +255,31 @@ def test_patch_attention_tensor_core(H, d, K, logits):
     assert excess_simt <= 0, excess_simt
     rel = ((got.float().cpu() - want).norm() / want.norm()).item()
     assert rel < 1e-2, rel
+
+
+@pytest.mark.parametrize("n,cin,cout", [(1, 16, 32), (300, 128, 32), (257, 256, 64), (5001, 3072, 768), (40001, 2048, 512)])
+@pytest.mark.parametrize("inplace", [True, False])
+def test_linear_residual_cta_pair(n, cin, cout, inplace):
+    """fc2 + bias + residual add in the GEMM epilogue (csrc/gemm2cta.cu, RES = 1) vs float64 on the same bf16 operands:
+    the fp32 result carries only the accumulation-order error of an fp32 dot product of `cin` bf16 products
+    (|err| <= 2e-5 * sqrt(cin) * scale), the bf16 copy is its correctly rounded value."""
+    from scenesplat_b200 import ops
+    torch.manual_seed(n + cin)
+    x = torch.randn(n, cin).bfloat16()
+    w = (torch.randn(cout, cin) / cin ** 0.5).bfloat16()
+    b = torch.randn(cout)
+    res = torch.randn(n, cout) * 3
+    want = res.double() + x.double() @ w.double().t() + b.double()
+    r = res.cuda()
+    out, shadow = ops.linear_residual(x.cuda(), w.cuda(), b.cuda(), r, inplace=inplace)
+    assert (out.data_ptr() == r.data_ptr()) == inplace
+    if not inplace:
+        assert torch.equal(r.cpu(), res)  # untouched
+    err = (out.double().cpu() - want).abs().max().item()
+    assert err <= 2e-5 * cin ** 0.5 * 4, err
+    assert torch.equal(shadow, out.bfloat16())
+    out2, none = ops.linear_residual(x.cuda(), w.cuda(), b.cuda(), res.cuda(), want_bf16=False)
+    assert none is None and torch.equal(out2, out)
 
 
 @pytest.mark.parametrize("n,cin,cout", [(1, 16, 32), (255, 48, 96), (257, 64, 256), (1000, 768, 3072), (5001, 3072, 768),
