@@ -295,6 +295,30 @@ int ss_class_half_sums(const void* pred, int pred_is_bf16, const uint8_t* mask, 
                        const int64_t* half, int64_t n, int channels, int n_classes, float* sums, int32_t* counts,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Adjoints of the pooling / unpooling reductions and of the language losses (training; csrc/pool_loss_bwd.cu). */
+
+/* d src of the segment mean (reduce = 1) / sum (reduce = 0) of SerializedPooling (autograd through
+ * torch_scatter.segment_csr, point_transformer_v3m1_base.py:416-418): dsrc[p,:] = dout[cluster[p],:] (/ count). */
+int ss_segment_mean_bwd(const void* dout, int dout_is_bf16, const int64_t* cluster, const int64_t* seg_start, int64_t n,
+                        int channels, int reduce, void* dsrc, int dsrc_is_bf16, void* stream);
+
+/* d child of SerializedUnpooling's gather `point.feat[inverse]` (ref :478): dchild[m,:] = sum over the members of cluster
+ * m (positions seg_start[m] .. seg_start[m+1] of order0) of dout[p,:]; deterministic segment sum. */
+int ss_unpool_gather_add_bwd(const void* dout, int dout_is_bf16, const int64_t* order0, const int64_t* seg_start, int64_t m,
+                             int channels, void* dchild, int dchild_is_bf16, void* stream);
+
+/* d pred of w_cos * sum_valid(1 - cos) / n_valid + w_l2 * sum_valid ||pred - target||^2 / n_valid (losses/misc.py:254-295)
+ * times *grad_out (device scalar, NULL = 1).  acc3 = the double[3] ss_cos_l2_loss wrote (n_valid is read from it on the
+ * device).  Rows with mask == 0 get zeros.  dpred fp32 [n, channels]. */
+int ss_cos_l2_loss_bwd(const void* pred, int pred_is_bf16, const void* target, int target_dtype, const uint8_t* mask,
+                       int64_t n, int channels, const double* acc3, const float* grad_out, float w_cos, float w_l2,
+                       float* dpred, void* stream);
+
+/* d pred of ss_class_half_sums: dpred[p,:] = dsums[segment[p] * 2 + half[p], :] for valid rows, else 0. */
+int ss_class_half_sums_bwd(const float* dsums, const uint8_t* mask, const int64_t* segment, const int64_t* half, int64_t n,
+                           int channels, int n_classes, float* dpred, void* stream);
+
 /* Library / build identification; number of kernels this library has launched in the process. */
 const char* ss_version(void);
 uint64_t ss_launch_count(void);

@@ -171,12 +171,14 @@ class _SubMConv3d(nn.Module):
         k3 = self.kernel_size ** 3
         w = self.weight.reshape(self.out_channels, k3, self.in_channels)
         out = feat.new_zeros(feat.shape[0], self.out_channels)
-        for t in range(k3):
-            col = nbr[:, t]
-            rows = (col >= 0).nonzero(as_tuple=True)[0]
-            if rows.numel() == 0:
-                continue
-            out.index_add_(0, rows, feat[col[rows]] @ w[:, t, :].t())
+        # spconv is a custom op: autocast does not touch it (the SSL variant only runs under AMP)
+        with torch.autocast(device_type=feat.device.type, enabled=False):
+            for t in range(k3):
+                col = nbr[:, t]
+                rows = (col >= 0).nonzero(as_tuple=True)[0]
+                if rows.numel() == 0:
+                    continue
+                out.index_add_(0, rows, feat[col[rows]] @ w[:, t, :].t().to(feat.dtype))
         if self.bias is not None:
             out = out + self.bias
         return x.replace_feature(out)
@@ -194,6 +196,11 @@ def _install_shims():
         m.layers = ml
         sys.modules["timm"] = m
         sys.modules["timm.layers"] = ml
+        mm_ = types.ModuleType("timm.models")  # the SSL variant imports DropPath from timm.models.layers
+        mm_.layers = ml
+        m.models = mm_
+        sys.modules["timm.models"] = mm_
+        sys.modules["timm.models.layers"] = ml
     if "torch_scatter" not in sys.modules:
         m = types.ModuleType("torch_scatter")
         m.segment_csr = _segment_csr
@@ -258,6 +265,18 @@ def load_reference():
         kernel_map_dense=_kernel_map_dense,
     )
     return types.SimpleNamespace(**_LOADED)
+
+
+def load_reference_ssl():
+    """The reference's self-supervised PT-v3m1 (point_transformer_v3_ssl/point_transformer_v3m1_ssl.py), unmodified."""
+    load_reference()
+    pkg = "pointcept.models.point_transformer_v3_ssl"
+    if pkg not in sys.modules:
+        m = types.ModuleType(pkg)
+        m.__path__ = [os.path.join(REFERENCE_ROOT, "pointcept/models/point_transformer_v3_ssl")]
+        sys.modules[pkg] = m
+    mod = importlib.import_module(pkg + ".point_transformer_v3m1_ssl")
+    return mod.PointTransformerV3_SIMDINO
 
 
 LANG_BACKBONE_CFG = dict(

@@ -6,8 +6,8 @@ Importing the package does not touch the GPU; the first kernel call loads the in
 """
 from .registry import LOSSES, MODELS, TRANSFORMS, build_model, register_into_pointcept  # noqa: F401
 from .structure import Point  # noqa: F401
-from .ptv3 import (Block, Embedding, MLP, PointTransformerV3, SerializedAttention, SerializedPooling,  # noqa: F401
-                   SerializedUnpooling)
+from .ptv3 import (Block, Embedding, MLP, PointTransformerV3, PointTransformerV3SimDINO, SerializedAttention,  # noqa: F401
+                   SerializedPooling, SerializedUnpooling)
 from .lang import (AggregatedContrastiveLoss, ChunkPipeline, CosineSimilarity, Criteria, L2Loss,  # noqa: F401
                    LangPretrainer, zero_shot_accumulate, zero_shot_labels)
 from .transform import GridSample, SphereCrop  # noqa: F401

@@ -56,6 +56,10 @@ SIGNATURES = {
     "ss_lang_head_tc": (_i, [_vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "ss_cos_l2_loss": (_i, [_vp, _i, _vp, _i, _vp, _i64, _i, _vp, _vp]),
     "ss_class_half_sums": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "ss_segment_mean_bwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _i, _vp, _i, _vp]),
+    "ss_unpool_gather_add_bwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp, _i, _vp]),
+    "ss_cos_l2_loss_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp]),
+    "ss_class_half_sums_bwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),
     "ss_gelu_backward_bf16": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "ss_subm_conv_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ss_layernorm_backward": (_i, [_vp, _i, _vp, _i, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp]),

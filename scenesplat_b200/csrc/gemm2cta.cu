@@ -149,13 +149,18 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       tc::mbar_wait(&acc_full[b], (uint32_t)((it >> 1) & 1));
       tc::tc_fence_after();
       const int64_t row0 = tile * kPTileM + rank * 128 + quarter * 32;
-#pragma unroll 1
+      // 32-column groups of this warp inside the matrix; the TMEM load of group j + 1 is in flight while group j is
+      // converted and stored (two register buffers, loop fully unrolled)
+      const int nj = max(0, min(4, (cout - (n0 + half * 128) + 31) / 32));
+      uint32_t vbuf[2][32];
+      if (RES == 0 && nj > 0) tc::tmem_ld32(t_lane + b * kPTileN + half * 128, vbuf[0]);
+#pragma unroll
       for (int j = 0; j < 4; ++j) {
+        if (j >= nj) break;
         const int c0 = n0 + half * 128 + j * 32;
-        if (c0 >= cout) break;
-        uint32_t v[32];
-        tc::tmem_ld32(t_lane + b * kPTileN + half * 128 + j * 32, v);
+        uint32_t (&v)[32] = vbuf[RES == 1 ? 0 : (j & 1)];
         if constexpr (RES == 1) {
+          tc::tmem_ld32(t_lane + b * kPTileN + half * 128 + j * 32, v);
           // residual tile -> shared memory with coalesced 128-byte row segments (8 lanes per row, 4 rows per access)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -199,6 +204,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           }
         } else {
         tc::tmem_ld_wait();
+        if (j + 1 < nj) tc::tmem_ld32(t_lane + b * kPTileN + half * 128 + (j + 1) * 32, vbuf[(j + 1) & 1]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];

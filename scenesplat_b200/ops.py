@@ -548,3 +548,50 @@ def class_half_sums(pred, mask, segment, half, n_classes: int):
     L.call("ss_class_half_sums", L.ptr(pred), _isbf(pred), L.ptr(m8), L.ptr(seg64),
            L.ptr(half64), n, c, n_classes, L.ptr(sums), L.ptr(counts), L.stream())
     return sums, counts
+
+
+# ------------------------------------------------------------------------------------------- adjoints (training)
+def _mask8(mask):
+    return mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous().to(torch.uint8)
+
+
+def segment_mean_backward(dout, cluster, seg_start, reduce="mean", out_dtype=None):
+    """d src of segment_reduce(src, order0, seg_start, "mean" | "sum"): dsrc[p] = dout[cluster[p]] (/ count)."""
+    dout = dout.contiguous()
+    n, c = cluster.shape[0], dout.shape[1]
+    dsrc = torch.empty((n, c), dtype=out_dtype or dout.dtype, device=dout.device)
+    cluster, seg_start = _i64(cluster).contiguous(), _i64(seg_start).contiguous()
+    L.call("ss_segment_mean_bwd", L.ptr(dout), _isbf(dout), L.ptr(cluster), L.ptr(seg_start), n, c, _REDUCE[reduce], L.ptr(dsrc),
+           _isbf(dsrc), L.stream())
+    return dsrc
+
+
+def unpool_gather_add_backward(dout, order0, seg_start, out_dtype=None):
+    """d child of out = a + child[cluster]: the segment sum of dout over each cluster's members."""
+    dout = dout.contiguous()
+    m, c = seg_start.shape[0] - 1, dout.shape[1]
+    dchild = torch.empty((m, c), dtype=out_dtype or dout.dtype, device=dout.device)
+    order0, seg_start = _i64(order0).contiguous(), _i64(seg_start).contiguous()
+    L.call("ss_unpool_gather_add_bwd", L.ptr(dout), _isbf(dout), L.ptr(order0), L.ptr(seg_start), m, c, L.ptr(dchild),
+           _isbf(dchild), L.stream())
+    return dchild
+
+
+def cos_l2_backward(pred, target, mask, acc, grad_out, w_cos, w_l2):
+    """d pred (fp32) of w_cos * mean_valid(1 - cos) + w_l2 * mean_valid ||pred - target||^2, times the device scalar grad_out."""
+    pred, target, m8 = pred.contiguous(), target.contiguous(), _mask8(mask)
+    n, c = pred.shape
+    dpred = torch.empty((n, c), dtype=torch.float32, device=pred.device)
+    g = grad_out.reshape(1).float().contiguous() if grad_out is not None else None
+    L.call("ss_cos_l2_loss_bwd", L.ptr(pred), _isbf(pred), L.ptr(target), _TGT[target.dtype], L.ptr(m8), n, c, L.ptr(acc), L.ptr(g),
+           float(w_cos), float(w_l2), L.ptr(dpred), L.stream())
+    return dpred
+
+
+def class_half_sums_backward(dsums, mask, segment, half, n_classes: int):
+    dsums = dsums.contiguous().float()
+    m8, seg64, half64 = _mask8(mask), _i64(segment).contiguous(), _i64(half).contiguous()
+    n, c = seg64.shape[0], dsums.shape[1]
+    dpred = torch.empty((n, c), dtype=torch.float32, device=dsums.device)
+    L.call("ss_class_half_sums_bwd", L.ptr(dsums), L.ptr(m8), L.ptr(seg64), L.ptr(half64), n, c, n_classes, L.ptr(dpred), L.stream())
+    return dpred

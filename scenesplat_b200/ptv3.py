@@ -525,6 +525,7 @@ class PointTransformerV3(PointModule):
         assert self.cls_mode or self.num_stages == len(dec_patch_size) + 1
         if pdnorm_bn or pdnorm_ln:
             raise NotImplementedError("PDNorm is disabled in every SceneSplat lang config and is out of scope here")
+        self._before_layers(enc_channels)  # (sub-classes register parameters that precede the layers in the reference)
         bn_layer = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
         ln_layer = nn.LayerNorm
         act_layer = nn.GELU
@@ -538,7 +539,8 @@ class PointTransformerV3(PointModule):
             enc = PointSequential()
             if s > 0:
                 enc.add(SerializedPooling(in_channels=enc_channels[s - 1], out_channels=enc_channels[s],
-                                          stride=stride[s - 1], norm_layer=bn_layer, act_layer=act_layer), name="down")
+                                          stride=stride[s - 1], norm_layer=bn_layer, act_layer=act_layer,
+                                          reduce=self._pooling_reduce()), name="down")
             for i in range(enc_depths[s]):
                 enc.add(Block(channels=enc_channels[s], num_heads=enc_num_head[s], patch_size=enc_patch_size[s],
                               mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop,
@@ -548,7 +550,7 @@ class PointTransformerV3(PointModule):
                               upcast_softmax=upcast_softmax), name=f"block{i}")
             if len(enc) != 0:
                 self.enc.add(module=enc, name=f"enc{s}")
-        if not self.cls_mode:
+        if self._has_decoder():
             dec_drop_path = [x.item() for x in torch.linspace(0, drop_path, sum(dec_depths))]
             self.dec = PointSequential()
             dec_channels = list(dec_channels) + [enc_channels[-1]]
@@ -567,6 +569,16 @@ class PointTransformerV3(PointModule):
                                   cpe_indice_key=f"stage{s}", enable_rpe=enable_rpe, enable_flash=enable_flash,
                                   upcast_attention=upcast_attention, upcast_softmax=upcast_softmax), name=f"block{i}")
                 self.dec.add(module=dec, name=f"dec{s}")
+
+    # hooks of the SSL variant (PointTransformerV3SimDINO)
+    def _before_layers(self, enc_channels):
+        pass
+
+    def _pooling_reduce(self):
+        return "mean"
+
+    def _has_decoder(self):
+        return not self.cls_mode
 
     def plan_indices(self, point):
         """Builds the whole feature-independent index hierarchy up front: pooled codes / orders / clusters of every
@@ -624,3 +636,53 @@ class PointTransformerV3(PointModule):
             from . import training
             return Point(Dict(feat=training.forward_train(self, data_dict)))
         return self.run(self.prepare(data_dict))
+
+
+@MODELS.register_module("PT-v3m1-simdino")
+class PointTransformerV3SimDINO(PointTransformerV3):
+    """The self-supervised variant of PT-v3m1 (pointcept/models/point_transformer_v3_ssl/point_transformer_v3m1_ssl.py:
+    532-790, registered as "PT-v3m1-simdino"): same encoder / decoder modules and `state_dict` keys, plus
+      * `do_mask`: a learnable `mask_token` [1, enc_channels[0]] that replaces the embedded features of masked points
+        (ref :585-592, :768-772); the decoder exists only when do_mask is set (ref :676);
+      * `pooling_reduce` (default "max") for every SerializedPooling (ref :359, :644);
+      * `forward(data_dict, mask=None, return_dec=False)` -> (Point(feat, offset) of the encoder output, decoder Point or
+        None) (ref :759-790).
+    Inference path (the SSL losses / teacher-student training loop of the reference are outside the hot path)."""
+
+    def __init__(self, *args, do_mask=False, pooling_reduce="max", **kwargs):
+        self.do_mask, self.pooling_reduce = do_mask, pooling_reduce
+        super().__init__(*args, **kwargs)
+
+    def __setattr__(self, name, value):
+        # do_mask / pooling_reduce are set before nn.Module.__init__ ran (the hooks below need them during construction)
+        if name in ("do_mask", "pooling_reduce") and "_parameters" not in self.__dict__:
+            object.__setattr__(self, name, value)
+        else:
+            super().__setattr__(name, value)
+
+    def _before_layers(self, enc_channels):
+        if self.do_mask:  # created before the layers, like the reference: same RNG stream, same state_dict order
+            mask_token = torch.nn.Parameter(torch.zeros(1, enc_channels[0]))
+            torch.nn.init.trunc_normal_(mask_token, std=0.02)
+            self.mask_token = mask_token
+
+    def _pooling_reduce(self):
+        return self.pooling_reduce
+
+    def _has_decoder(self):
+        return bool(self.do_mask)
+
+    def forward(self, data_dict, mask=None, return_dec=False):
+        if torch.is_grad_enabled() and self.training:
+            raise NotImplementedError("PT-v3m1-simdino: only the inference path is built (SURVEY.md 8f, row 4)")
+        point = self.prepare(data_dict)
+        point = self.embedding(point)
+        if mask is not None:
+            # ref :768-772: in place on the tensor that point.feat AND sparse_conv_feat.features share
+            feat = point.feat
+            feat[mask] = self.mask_token.to(device=feat.device, dtype=feat.dtype)
+            point.feat = feat
+        point = self.enc(point)
+        point_enc = Point(Dict(feat=point.feat, offset=point.offset))
+        point_dec = self.dec(point) if return_dec else None
+        return point_enc, point_dec

@@ -220,21 +220,69 @@ class SegmentMeanFn(torch.autograd.Function):
     """out[m] = mean_{j in [seg_start[m], seg_start[m+1])} src[order0[j]]   (replaces torch_scatter.segment_csr)."""
 
     @staticmethod
-    def forward(ctx, src, order0, seg_start):
+    def forward(ctx, src, order0, seg_start, cluster):
         out = ops.segment_reduce(src, order0, seg_start, "mean", out_dtype=torch.float32)
+        ctx.save_for_backward(seg_start, cluster)
+        ctx.dtype = src.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        seg_start, cluster = ctx.saved_tensors
+        # dsrc[p] = dout[cluster[p]] / count[cluster[p]]: one gather kernel (csrc/pool_loss_bwd.cu)
+        return ops.segment_mean_backward(dout, cluster, seg_start, "mean", out_dtype=ctx.dtype), None, None, None
+
+
+class UnpoolGatherAddFn(torch.autograd.Function):
+    """out = a + child[cluster]  (ref :478, `parent.feat + point.feat[inverse]`).  Backward: da = dout, dchild = the
+    deterministic segment sum of dout over each cluster's members (torch's index backward is an atomic index_add)."""
+
+    @staticmethod
+    def forward(ctx, a, child, cluster, order0, seg_start):
+        out, _ = ops.unpool_gather_add(a.contiguous(), child.contiguous().to(a.dtype), cluster, out_dtype=a.dtype)
         ctx.save_for_backward(order0, seg_start)
-        ctx.shape, ctx.dtype = src.shape, src.dtype
+        ctx.child_dtype = child.dtype
         return out
 
     @staticmethod
     def backward(ctx, dout):
         order0, seg_start = ctx.saved_tensors
-        cnt = seg_start[1:] - seg_start[:-1]
-        seg = torch.repeat_interleave(torch.arange(cnt.numel(), device=dout.device), cnt, output_size=ctx.shape[0])
-        d = (dout / cnt.clamp(min=1)[:, None].to(dout.dtype))[seg]
-        dsrc = torch.empty(ctx.shape, dtype=ctx.dtype, device=dout.device)
-        dsrc[order0] = d.to(ctx.dtype)
-        return dsrc, None, None
+        return dout, ops.unpool_gather_add_backward(dout, order0, seg_start, out_dtype=ctx.child_dtype), None, None, None
+
+
+class CosL2LossFn(torch.autograd.Function):
+    """w_cos * mean_valid(1 - cos(pred, target)) + w_l2 * mean_valid ||pred - target||^2 (losses/misc.py:254-295) with the
+    fused forward (ss_cos_l2_loss) and its one-pass adjoint (ss_cos_l2_loss_bwd); the valid count never leaves the device."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mask, w_cos, w_l2):
+        acc = ops.cos_l2_sums(pred, target, mask)
+        ctx.save_for_backward(pred, target, mask, acc)
+        ctx.w = (float(w_cos), float(w_l2))
+        n_valid = acc[2].clamp(min=1.0)
+        return ((w_cos * acc[0] + w_l2 * acc[1]) / n_valid).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target, mask, acc = ctx.saved_tensors
+        return ops.cos_l2_backward(pred, target, mask, acc, g, *ctx.w).to(pred.dtype), None, None, None, None
+
+
+class ClassHalfSumsFn(torch.autograd.Function):
+    """Per (class, half) feature sums of AggregatedContrastiveLoss (misc.py:384-385) and their adjoint (a row gather)."""
+
+    @staticmethod
+    def forward(ctx, pred, valid, segment, half, n_classes):
+        sums, counts = ops.class_half_sums(pred, valid, segment, half, n_classes)
+        ctx.save_for_backward(valid, segment, half)
+        ctx.n_classes, ctx.dtype = n_classes, pred.dtype
+        ctx.mark_non_differentiable(counts)
+        return sums, counts
+
+    @staticmethod
+    def backward(ctx, dsums, _dcounts):
+        valid, segment, half = ctx.saved_tensors
+        return ops.class_half_sums_backward(dsums, valid, segment, half, ctx.n_classes).to(ctx.dtype), None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------ model walk
@@ -378,7 +426,7 @@ def pooling_train(down, point, x):
     if down.reduce != "mean":
         raise NotImplementedError("training path: SerializedPooling(reduce='mean') only (the lang configs)")
     order0 = point.serialized_order[0].contiguous()
-    feat = SegmentMeanFn.apply(_lin(down.proj, x), order0, ix["seg_start"])
+    feat = SegmentMeanFn.apply(_lin(down.proj, x), order0, ix["seg_start"], ix["cluster"])
     coord = ops.segment_reduce(point.coord.float(), order0, ix["seg_start"], "mean")
     names = point.serialized_order_names
     n_batch = point.offset.numel()
@@ -394,11 +442,13 @@ def pooling_train(down, point, x):
         feat = _bn(down.norm[0], feat)
     if getattr(down, "act", None) is not None:
         feat = F.gelu(feat)
-    return child, feat, ix["cluster"]
+    return child, feat, (ix["cluster"], order0, ix["seg_start"])
 
 
-def unpool_train(up, x_child, cluster, x_parent):
-    """SerializedUnpooling.forward (ref :471-482) under autograd -> (parent feat, skip branch alone)."""
+def unpool_train(up, x_child, pool_ix, x_parent):
+    """SerializedUnpooling.forward (ref :471-482) under autograd -> (parent feat, skip branch alone).  pool_ix = the
+    (cluster, order0, seg_start) of the pooling this level came from."""
+    cluster, order0, seg_start = pool_ix
     lin_p, bn_p, act_p, _ = up._branch(up.proj)
     lin_s, bn_s, act_s, _ = up._branch(up.proj_skip)
     a = _bn(bn_p, _lin(lin_p, x_child).float())
@@ -407,7 +457,7 @@ def unpool_train(up, x_child, cluster, x_parent):
         a = F.gelu(a)
     if act_s is not None:
         s = F.gelu(s)
-    return s + a[cluster], s
+    return UnpoolGatherAddFn.apply(s, a, cluster, order0, seg_start), s
 
 
 def forward_train(model, data_dict):
@@ -446,9 +496,16 @@ def forward_train(model, data_dict):
 
 
 # ------------------------------------------------------------------------------------------------ losses (autograd)
+def _fused_loss_ok(pred, target):
+    return pred.is_cuda and pred.dim() == 2 and pred.shape[1] % 8 == 0 and pred.dtype in (torch.float32, BF16) and \
+        target.dtype in (torch.float32, BF16, torch.float16)
+
+
 def cosine_loss(pred, target, mask, loss_weight=1.0):
-    """losses/misc.py:254-270: mean over the valid rows of 1 - cos.  Masked arithmetic over all rows instead of boolean
-    indexing, so nothing synchronises the stream between forward and backward (no valid row -> 0)."""
+    """losses/misc.py:254-270: mean over the valid rows of 1 - cos: fused forward + adjoint kernels (no boolean
+    indexing, no host decision; no valid row -> 0).  Shapes the kernels do not take use the torch formulation below."""
+    if _fused_loss_ok(pred, target):
+        return CosL2LossFn.apply(pred, target, mask.reshape(-1), float(loss_weight), 0.0)
     m = mask.reshape(-1).bool()
     cos = F.cosine_similarity(pred.float(), target.float(), dim=1, eps=1e-8)
     n_valid = m.sum().clamp(min=1).to(cos.dtype)
@@ -456,7 +513,9 @@ def cosine_loss(pred, target, mask, loss_weight=1.0):
 
 
 def l2_loss(pred, target, mask, loss_weight=1.0):
-    """losses/misc.py:280-295: mean over the valid rows of the squared distance (same masking as cosine_loss)."""
+    """losses/misc.py:280-295: mean over the valid rows of the squared distance (same kernels as cosine_loss)."""
+    if _fused_loss_ok(pred, target):
+        return CosL2LossFn.apply(pred, target, mask.reshape(-1), 0.0, float(loss_weight))
     m = mask.reshape(-1).bool()
     d2 = ((pred.float() - target.float()) ** 2).sum(1)
     n_valid = m.sum().clamp(min=1).to(d2.dtype)
@@ -488,7 +547,11 @@ def contrastive_from_sums(sums, counts, n_classes, temperature, reduction="mean"
 
 
 def class_half_sums(pred, valid, segment, half, n_classes):
-    """Per (class, half) feature sums with torch index_add (differentiable twin of ops.class_half_sums)."""
+    """Per (class, half) feature sums under autograd: the fused kernel + its gather adjoint; torch index_add for shapes
+    the kernel does not take."""
+    if pred.is_cuda and pred.shape[1] % 8 == 0 and pred.dtype in (torch.float32, BF16):
+        sums, counts = ClassHalfSumsFn.apply(pred, valid, segment, half, n_classes)
+        return sums, counts.long()
     key = segment.long().clamp(min=0) * 2 + half.long()
     w = valid.to(pred.dtype)[:, None]
     sums = pred.new_zeros(2 * n_classes, pred.shape[1]).index_add(0, key, pred * w)

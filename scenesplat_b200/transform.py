@@ -94,10 +94,10 @@ class GridSample(object):
 
 @TRANSFORMS.register_module()
 class SphereCrop(object):
-    """Drop-in for pointcept/datasets/transform.py:1419-1535 (modes "random" and "center"; "all" is the test-time
-    multi-crop generator and is not built).  The distance ranking runs on the GPU (csrc/crop.cu), every per-point
-    array of the dict is gathered on the device.  The random centre index is drawn from numpy's global RNG exactly
-    like the reference (`np.random.randint(N)`)."""
+    """Drop-in for pointcept/datasets/transform.py:1419-1535, modes "random", "center" and "all" (the test-time multi-crop
+    generator, ref :1439-1503).  The distance ranking runs on the GPU (csrc/crop.cu), every per-point array of the dict
+    is gathered on the device.  Random numbers are drawn from numpy's global RNG exactly like the reference
+    (`np.random.randint(N)`; for "all" `np.random.rand(N) * 1e-3`)."""
 
     # every key the reference crops (transform.py:1500-1534), plus `index` if present
     KEYS = ("coord", "origin_coord", "grid_coord", "color", "quat", "scale", "opacity", "normal", "lang_feat",
@@ -105,14 +105,54 @@ class SphereCrop(object):
 
     def __init__(self, point_max=80000, sample_rate=None, mode="random", device="cuda"):
         assert mode in ["random", "center", "all"]
-        if mode == "all":
-            raise NotImplementedError("SphereCrop(mode='all') (test-time multi-crop) is not built")
         self.point_max, self.sample_rate, self.mode, self.device = point_max, sample_rate, mode, device
+
+    # keys the reference copies into every crop of mode "all" (ref :1462-1491)
+    ALL_KEYS = ("coord", "grid_coord", "normal", "color", "opacity", "quat", "lang_feat", "valid_feat_mask", "scale",
+                "displacement", "strength")
+
+    def _crop_all(self, data_dict, point_max):
+        """ref :1439-1503: crops of the `point_max` nearest points around successive seeds until every point is covered;
+        the next seed is the point with the smallest priority, and a crop raises the priority of its members by
+        (1 - dist2 / max dist2)^2.  Returns a list of dicts (with `weight` = dist2 and `index`)."""
+        n = data_dict["coord"].shape[0]
+        as_numpy = isinstance(data_dict["coord"], np.ndarray)
+        to_dev = lambda v: (torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v).to(self.device)
+        back = (lambda t: t.cpu().numpy()) if as_numpy else (lambda t: t)
+        if "index" not in data_dict.keys():
+            data_dict["index"] = np.arange(n) if as_numpy else torch.arange(n, device=self.device)
+        if n <= point_max:
+            part = dict(data_dict)
+            part["weight"] = np.zeros(n) if as_numpy else torch.zeros(n, dtype=torch.float64, device=self.device)
+            return [part]
+        coord = to_dev(data_dict["coord"]).float().contiguous()
+        index = to_dev(data_dict["index"])
+        dev = {k: to_dev(data_dict[k]) for k in self.ALL_KEYS if k in data_dict.keys()}
+        prio = torch.from_numpy(np.random.rand(n) * 1e-3).to(self.device)  # float64, the reference's `coord_p`
+        covered = torch.zeros(n, dtype=torch.bool, device=self.device)
+        parts = []
+        while not bool(covered.all()):
+            init = int(torch.argmin(prio))
+            center = coord[init]
+            order = ops.sphere_crop_order(coord, center.cpu())
+            idx_crop = order[:point_max].contiguous()
+            part = {k: back(ops.gather_rows(v, idx_crop)) for k, v in dev.items()}
+            d = coord[idx_crop] - center
+            dist2 = (d * d).sum(1)  # fp32, like numpy on float32 coordinates
+            part["weight"] = back(dist2)
+            part["index"] = back(index[idx_crop])
+            parts.append(part)
+            # numpy: float32 `weight` -> float32 delta, added into the float64 priorities
+            prio[idx_crop] += torch.square(1.0 - dist2 / dist2.max()).double()
+            covered[idx_crop] = True
+        return parts
 
     def __call__(self, data_dict):
         assert "coord" in data_dict.keys()
         n = data_dict["coord"].shape[0]
         point_max = int(self.sample_rate * n) if self.sample_rate is not None else self.point_max
+        if self.mode == "all":
+            return self._crop_all(data_dict, point_max)
         if n <= point_max:
             return data_dict
         as_numpy = isinstance(data_dict["coord"], np.ndarray)

@@ -233,6 +233,43 @@ def gen_ptv3_small(ref):
     save("ptv3_small.npz", **arrs)
 
 
+def gen_ptv3_ssl(ref):
+    """PT-v3m1-simdino (point_transformer_v3m1_ssl.py:532-790): mask token, max pooling, (encoder, decoder) outputs."""
+    from oracle.ref_shim import load_reference_ssl
+    SSL = load_reference_ssl()
+    d = synthetic.chunk(7000, L=2.2, H=1.6, seed=23)
+    gs = ref.GridSample(grid_size=0.02, hash_type="fnv", mode="train",
+                        keys=("coord", "color", "opacity", "quat", "scale"), return_grid_coord=True)
+    np.random.seed(1)
+    res = gs({k: v.copy() for k, v in d.items()})
+    n = res["coord"].shape[0]
+    feat = synthetic.feat_from(res)
+    offset = np.array([n // 3, n], dtype=np.int64)
+    torch.manual_seed(0)
+    model = SSL(**SMALL_CFG, do_mask=True, pooling_reduce="max").eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+        for p in list(model.parameters()) + list(model.buffers()):
+            if p.is_floating_point():
+                p.copy_(p.half().float())
+    mask = torch.from_numpy(np.random.default_rng(5).uniform(size=n) < 0.3)
+    data = dict(coord=torch.from_numpy(res["coord"]), grid_coord=torch.from_numpy(res["grid_coord"].astype(np.int64)),
+                feat=torch.from_numpy(feat), offset=torch.from_numpy(offset))
+    torch.manual_seed(2025)
+    # the reference Block casts `point.feat` to half unconditionally (ssl.py:330-331): it only runs under AMP
+    with torch.no_grad(), torch.autocast(device_type="cpu", dtype=torch.float16):
+        enc, dec = model(data, mask=mask, return_dec=True)
+    arrs = dict(coord=res["coord"], grid_coord=res["grid_coord"].astype(np.int64), feat=feat, offset=offset,
+                mask=mask.numpy(), enc_feat=enc.feat.float().numpy(), enc_offset=enc.offset.numpy(),
+                dec_feat=dec.feat.float().numpy())
+    for k, v in model.state_dict().items():
+        arrs["sd." + k] = v.numpy().astype(np.float16) if v.is_floating_point() else v.numpy()
+    save("ptv3_ssl.npz", **arrs)
+
+
 def gen_spherecrop(ref):
     """SphereCrop (transform.py:1419-1535), modes center and random, under a fixed numpy seed."""
     out = {}
@@ -256,8 +293,26 @@ def gen_spherecrop(ref):
     save("spherecrop.npz", **out)
 
 
+def gen_spherecrop_all(ref):
+    """SphereCrop(mode="all") (transform.py:1439-1503): the list of crops under a fixed numpy seed."""
+    import contextlib, io
+    d = synthetic.chunk(12000, L=3.0, H=2.0, seed=13)
+    coord = d["coord"]
+    np.random.seed(31)
+    sc = ref.SphereCrop(point_max=4000, mode="all")
+    with contextlib.redirect_stdout(io.StringIO()):  # (the reference prints the dict keys of every crop)
+        parts = sc(dict(coord=coord.copy(), color=d["color"].copy(), opacity=d["opacity"].copy()))
+    out = dict(coord_in=coord, color_in=d["color"], opacity_in=d["opacity"], n_parts=np.array(len(parts)))
+    for i, p in enumerate(parts):
+        out[f"p{i}_index"] = p["index"]
+        out[f"p{i}_weight"] = p["weight"]
+        out[f"p{i}_coord"] = p["coord"]
+        out[f"p{i}_color"] = p["color"]
+    save("spherecrop_all.npz", **out)
+
+
 if __name__ == "__main__":
     ref = load_reference()
-    which = sys.argv[1:] or ["serialization", "gridsample", "patch_table", "pooling", "losses", "ptv3_small", "spherecrop"]
+    which = sys.argv[1:] or ["serialization", "gridsample", "patch_table", "pooling", "losses", "ptv3_small", "ptv3_ssl", "spherecrop", "spherecrop_all"]
     for w in which:
         globals()["gen_" + w](ref)

@@ -311,3 +311,19 @@ def test_packed_scene_equals_reference_get_data(tmp_path, with_segment):
         f.truncate(size - 8192)
     with pytest.raises(IOError):
         sio.load_scene(packed, pinned=False)
+
+
+def test_ssl_variant_state_dict_matches_reference_golden_keys(golden):
+    """PT-v3m1-simdino: identical parameter names / shapes / order as the reference's PointTransformerV3_SIMDINO
+    (fixture generated from the unmodified reference file) and strict loading."""
+    import scenesplat_b200 as S
+    from tests.golden.make_golden import SMALL_CFG
+    g = golden("ptv3_ssl.npz")
+    ref_keys = [k[3:] for k in g.files if k.startswith("sd.")]
+    model = S.build_model(dict(type="PT-v3m1-simdino", do_mask=True, pooling_reduce="max", **SMALL_CFG))
+    sd = model.state_dict()
+    assert list(sd.keys()) == ref_keys
+    for k in ref_keys:
+        assert tuple(sd[k].shape) == tuple(g["sd." + k].shape), k
+    assert ref_keys[0] == "mask_token" and all(m.reduce == "max" for m in model.modules() if isinstance(m, S.SerializedPooling))
+    assert not hasattr(S.PointTransformerV3SimDINO(**SMALL_CFG, do_mask=False), "dec")  # decoder only with do_mask (ref :676)

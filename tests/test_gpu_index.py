@@ -346,3 +346,60 @@ def test_packed_scene_one_copy_to_device(tmp_path):
         assert got.is_cuda and tuple(got.shape) == v.shape, k
         np.testing.assert_array_equal(got.cpu().numpy(), v)
     assert dev_arrays["lang_feat"].dtype == torch.float16   # stays fp16 until a kernel reads it
+
+
+def test_sphere_crop_all_golden(golden):
+    """SphereCrop(mode="all") (test-time multi-crop, transform.py:1439-1503) vs the reference's own list of crops under
+    the same numpy seed: same number of crops, same member sets, bit-identical fp32 `weight` (squared distance to the
+    seed), same gathered attributes.  Members at exactly equal distance may be permuted (numpy's unstable argsort), so
+    each crop is compared as a set keyed by `index`."""
+    import scenesplat_b200 as S
+    g = golden("spherecrop_all.npz")
+    np.random.seed(31)
+    parts = S.SphereCrop(point_max=4000, mode="all")(dict(coord=g["coord_in"].copy(), color=g["color_in"].copy(),
+                                                         opacity=g["opacity_in"].copy()))
+    assert len(parts) == int(g["n_parts"])
+    covered = np.zeros(g["coord_in"].shape[0], dtype=bool)
+    for i, p in enumerate(parts):
+        assert set(p.keys()) == {"coord", "color", "opacity", "weight", "index"}
+        a, b = np.argsort(p["index"], kind="stable"), np.argsort(g[f"p{i}_index"], kind="stable")
+        np.testing.assert_array_equal(p["index"][a], g[f"p{i}_index"][b])
+        np.testing.assert_array_equal(p["weight"][a], g[f"p{i}_weight"][b])
+        np.testing.assert_array_equal(p["coord"][a], g[f"p{i}_coord"][b])
+        np.testing.assert_array_equal(p["color"][a], g[f"p{i}_color"][b])
+        assert np.all(np.diff(p["weight"]) >= 0)
+        covered[p["index"]] = True
+    assert covered.all()
+    # fewer points than point_max: one part holding everything, zero weights
+    small = S.SphereCrop(point_max=10 ** 6, mode="all")(dict(coord=g["coord_in"][:100].copy()))
+    assert len(small) == 1 and small[0]["weight"].shape == (100,) and not small[0]["weight"].any()
+    np.testing.assert_array_equal(small[0]["index"], np.arange(100))
+
+
+def test_lang_feat_stays_fp16_end_to_end():
+    """`lang_feat` is stored as fp16 on disk (datasets/scannetgs.py); the reference's ToTensor blows it up to fp32
+    (transform.py:390-391).  Here it stays fp16 through GridSample, SphereCrop and into the fused cosine / L2 losses
+    (forward and adjoint): same loss and same gradient as with an fp32 copy, at a quarter of the bytes."""
+    import scenesplat_b200 as S
+    from scenesplat_b200 import synthetic, training
+    d = synthetic.chunk(20000, L=2.4, H=1.6, seed=9, lang_dim=768)
+    assert d["lang_feat"].dtype == np.float16
+    gs = S.GridSample(grid_size=0.02, hash_type="fnv", mode="train",
+                      keys=("coord", "color", "opacity", "quat", "scale", "lang_feat", "valid_feat_mask", "segment"),
+                      return_grid_coord=True)
+    np.random.seed(0)
+    out = gs({k: torch.from_numpy(v) for k, v in d.items()})
+    np.random.seed(1)
+    out = S.SphereCrop(point_max=9000, mode="random")(out)
+    assert out["lang_feat"].dtype == torch.float16 and out["lang_feat"].is_cuda and out["lang_feat"].shape == (9000, 768)
+    torch.manual_seed(0)
+    res = {}
+    for name, tgt in (("fp16", out["lang_feat"]), ("fp32", out["lang_feat"].float())):
+        pred = torch.randn(9000, 768, device="cuda", generator=torch.Generator("cuda").manual_seed(4)).requires_grad_(True)
+        loss = training.cosine_loss(pred, tgt, out["valid_feat_mask"], 1.0) + training.l2_loss(pred, tgt, out["valid_feat_mask"], 1.0)
+        loss.backward()
+        res[name] = (loss.item(), pred.grad.clone())
+    assert abs(res["fp16"][0] - res["fp32"][0]) < 1e-6 * abs(res["fp32"][0])
+    assert torch.equal(res["fp16"][1], res["fp32"][1])
+    acc16 = S.CosineSimilarity()(torch.randn(9000, 768, device="cuda"), out["lang_feat"], out["valid_feat_mask"])
+    assert torch.isfinite(acc16)

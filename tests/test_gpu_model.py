@@ -232,3 +232,29 @@ def test_chunk_pipeline_distinct_large_chunks():
         assert len(got) == len(want)
         for i, (a, b) in enumerate(zip(got, want)):
             assert a.shape == b.shape and torch.equal(a, b), i
+
+
+def test_ssl_variant_golden(golden):
+    """PT-v3m1-simdino (mask token, max pooling, (encoder, decoder) outputs) against the UNMODIFIED reference model
+    (tests/golden/ptv3_ssl.npz; the reference variant only runs under AMP, so the fixture was produced under fp16
+    autocast: both sides carry 16-bit operand rounding, rel L2 < 4e-2 and mean row cosine > 0.999)."""
+    import scenesplat_b200 as S
+    from tests.golden.make_golden import SMALL_CFG
+    g = golden("ptv3_ssl.npz")
+    sd = {k[3:]: torch.from_numpy(g[k].astype(np.float32) if g[k].dtype == np.float16 else g[k])
+          for k in g.files if k.startswith("sd.")}
+    model = S.PointTransformerV3SimDINO(**SMALL_CFG, do_mask=True, pooling_reduce="max")
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    data = dict(coord=torch.from_numpy(g["coord"]).cuda(), grid_coord=torch.from_numpy(g["grid_coord"]).cuda(),
+                feat=torch.from_numpy(g["feat"]).cuda(), offset=torch.from_numpy(g["offset"]).cuda())
+    torch.manual_seed(2025)
+    with torch.no_grad():
+        enc, dec = model(data, mask=torch.from_numpy(g["mask"]).cuda(), return_dec=True)
+    np.testing.assert_array_equal(enc.offset.cpu().numpy(), g["enc_offset"])
+    for got, want in ((enc.feat, g["enc_feat"]), (dec.feat, g["dec_feat"])):
+        rel, cmean, cmin = _metrics(got, torch.from_numpy(want))
+        assert rel < 4e-2 and cmean > 0.999, (rel, cmean, cmin)
+    with torch.no_grad():
+        enc2, dec2 = model(data)  # no mask, encoder only
+    assert dec2 is None and enc2.feat.shape == enc.feat.shape

@@ -279,3 +279,101 @@ def test_stem_conv_wgrad_kernel():
     want = torch.matmul(xp[idx].transpose(1, 2), dy.double())  # [k3, cin, cout]
     err = (got.cpu().double() - want).abs().max()
     assert err <= 1e-4 * want.abs().max(), float(err)
+
+
+# ------------------------------------------------------------------------------------------------ adjoint kernels
+def _pool_setup(n=5000, seed=3):
+    """A pooling level on a random scene: (order0, seg_start, cluster, m) through the product's own index kernels."""
+    from scenesplat_b200 import ops
+    from oracle import serialization as oser
+    rng = np.random.default_rng(seed)
+    g = np.unique(rng.integers(0, 40, (n, 3)), axis=0)
+    n = g.shape[0]
+    batch = np.zeros(n, dtype=np.int64)
+    code, order, inv, depth = oser.serialization(g, batch, 1, ("z", "hilbert"))
+    dev = lambda a: torch.as_tensor(a).cuda()
+    ix = ops.pool_index(dev(code), dev(order), dev(g), dev(batch), 1, [0, 1])
+    return dev(order[0]).contiguous(), ix["seg_start"], ix["cluster"], ix["m"], n
+
+
+@pytest.mark.parametrize("c", [32, 64, 256])
+def test_segment_mean_and_unpool_adjoints(c):
+    """SegmentMeanFn / UnpoolGatherAddFn (csrc/pool_loss_bwd.cu) against torch autograd through the same reductions
+    written with index ops (fp32: equal up to summation order)."""
+    from scenesplat_b200 import training
+    order0, seg_start, cluster, m, n = _pool_setup()
+    torch.manual_seed(0)
+    src = torch.randn(n, c, device="cuda", requires_grad=True)
+    w = torch.randn(m, c, device="cuda")
+    out = training.SegmentMeanFn.apply(src, order0, seg_start, cluster)
+    (out * w).sum().backward()
+    src2 = src.detach().clone().requires_grad_(True)
+    cnt = torch.bincount(cluster, minlength=m).float()
+    ref = torch.zeros(m, c, device="cuda").index_add(0, cluster, src2) / cnt[:, None]
+    (ref * w).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(src.grad.cpu().numpy(), src2.grad.cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+    a = torch.randn(n, c, device="cuda", requires_grad=True)
+    child = torch.randn(m, c, device="cuda", requires_grad=True)
+    wo = torch.randn(n, c, device="cuda")
+    y = training.UnpoolGatherAddFn.apply(a, child, cluster, order0, seg_start)
+    (y * wo).sum().backward()
+    a2, child2 = a.detach().clone().requires_grad_(True), child.detach().clone().requires_grad_(True)
+    y2 = a2 + child2[cluster]
+    (y2 * wo).sum().backward()
+    np.testing.assert_allclose(y.detach().cpu().numpy(), y2.detach().cpu().numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), a2.grad.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(child.grad.cpu().numpy(), child2.grad.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("tdtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("pdtype", [torch.float32, torch.bfloat16])
+def test_cos_l2_loss_adjoint(pdtype, tdtype):
+    """CosL2LossFn against torch autograd through the reference's formulation (losses/misc.py:254-295: boolean-mask
+    gathers + nn.CosineSimilarity + squared distance), incl. fp16 targets (`lang_feat` as stored on disk) and the
+    no-valid-row case."""
+    from scenesplat_b200 import training
+    torch.manual_seed(1)
+    n, c = 3001, 768
+    pred = torch.randn(n, c, device="cuda").to(pdtype).requires_grad_(True)
+    target = torch.nn.functional.normalize(torch.randn(n, c, device="cuda"), dim=1).to(tdtype)
+    mask = torch.rand(n, device="cuda") < 0.8
+    up = torch.tensor(0.37, device="cuda")
+    loss = training.cosine_loss(pred, target, mask, 1.3) + training.l2_loss(pred, target, mask, 0.7)
+    (loss * up).backward()
+    p2 = pred.detach().float().clone().requires_grad_(True)
+    pv, tv = p2[mask], target.float()[mask]
+    ref = 1.3 * (1 - torch.nn.functional.cosine_similarity(pv, tv, dim=1)).sum() / mask.sum() + \
+        0.7 * ((pv - tv) ** 2).sum() / mask.sum()
+    (ref * up).backward()
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item()) + 1e-5
+    tol = 1e-6 if pdtype == torch.float32 else 2e-3  # the bf16 gradient is the fp32 one rounded to bf16
+    np.testing.assert_allclose(pred.grad.float().cpu().numpy(), p2.grad.cpu().numpy(), rtol=2e-2 if pdtype != torch.float32 else 1e-4,
+                               atol=tol)
+    # no valid row: loss 0, gradient 0
+    p3 = pred.detach().clone().requires_grad_(True)
+    l3 = training.cosine_loss(p3, target, torch.zeros_like(mask), 1.0)
+    l3.backward()
+    assert l3.item() == 0.0 and float(p3.grad.abs().max()) == 0.0
+
+
+def test_class_half_sums_adjoint():
+    from scenesplat_b200 import training
+    torch.manual_seed(2)
+    n, c, k = 4000, 768, 24
+    pred = torch.randn(n, c, device="cuda", requires_grad=True)
+    valid = torch.rand(n, device="cuda") < 0.7
+    segment = torch.randint(-1, k + 3, (n,), device="cuda")  # incl. ignore (-1) and labels past the class table
+    half = torch.randint(0, 2, (n,), device="cuda")
+    w = torch.randn(2 * k, c, device="cuda")
+    sums, counts = training.class_half_sums(pred, valid & (segment >= 0), segment, half, k)
+    (sums * w).sum().backward()
+    p2 = pred.detach().clone().requires_grad_(True)
+    ok = valid & (segment >= 0) & (segment < k)
+    key = (segment.clamp(0, k - 1) * 2 + half)
+    ref = torch.zeros(2 * k, c, device="cuda").index_add(0, key, p2 * ok[:, None])
+    (ref * w).sum().backward()
+    np.testing.assert_allclose(sums.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_array_equal(counts.cpu().numpy(), torch.bincount(key[ok], minlength=2 * k).cpu().numpy())
+    np.testing.assert_allclose(pred.grad.cpu().numpy(), p2.grad.cpu().numpy(), rtol=1e-6, atol=1e-6)
