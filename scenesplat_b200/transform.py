@@ -138,7 +138,8 @@ class SphereCrop(object):
             idx_crop = order[:point_max].contiguous()
             part = {k: back(ops.gather_rows(v, idx_crop)) for k, v in dev.items()}
             d = coord[idx_crop] - center
-            dist2 = (d * d).sum(1)  # fp32, like numpy on float32 coordinates
+            sq = d * d  # numpy: np.sum(np.power(coord - c, 2), 1) = ((x^2 + y^2) + z^2), every step rounded to fp32
+            dist2 = (sq[:, 0] + sq[:, 1]) + sq[:, 2]
             part["weight"] = back(dist2)
             part["index"] = back(index[idx_crop])
             parts.append(part)
