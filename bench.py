@@ -485,6 +485,8 @@ def main():
     if not args.no_extras:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import workloads as W
+        from scenesplat_b200 import inference
+        reserve(8 << 30, inference.pipeline_for(model, dev).side)  # the sweep's pipeline (one side stream per model)
 
         def guarded(name, fn):
             try:

@@ -16,6 +16,7 @@ Everything here is host orchestration over the package's kernels; there is no CP
 from __future__ import annotations
 
 import time
+import weakref
 
 import numpy as np
 import torch
@@ -108,6 +109,18 @@ def scene_chunks(coord, chunk_range=(6.0, 6.0), chunk_stride=(3.0, 3.0), chunk_m
 
 
 # ----------------------------------------------------------------------------------------------- sharded sweep
+_PIPES = weakref.WeakKeyDictionary()  # one ChunkPipeline (= one side stream = one allocator pool) per model
+
+
+def pipeline_for(model, device=None):
+    """The model's ChunkPipeline, created once: torch's caching allocator keeps a pool per stream, so a new side
+    stream per call would map fresh device memory for every scene (measured: 2x slower, erratic passes)."""
+    pipe = _PIPES.get(model)
+    if pipe is None:
+        pipe = _PIPES[model] = ChunkPipeline(model, device)
+    return pipe
+
+
 def sharded_chunk_labels(model, chunks, text, rank=0, world=1, policy="lpt", group=None, gather=True):
     """chunks: list of dicts (coord, grid_coord, feat, offset) -- pinned host or device tensors; every rank holds the
     same list (or at least the same sizes) and runs only its share.  Returns (labels per chunk: list of int32 tensors
@@ -118,7 +131,7 @@ def sharded_chunk_labels(model, chunks, text, rank=0, world=1, policy="lpt", gro
     dev = next(model.parameters()).device
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     labels = {}
-    pipe = ChunkPipeline(model, dev)
+    pipe = pipeline_for(model, dev)
     e0.record()
     for i, feat in zip(mine, pipe.map(chunks[i] for i in mine)):
         _, lab = zero_shot_labels(feat, text)
