@@ -454,7 +454,7 @@ def main():
     own_ms = sum(r["ms"] for r in own.values()) / prof_steps
     # the second half of BASELINE.json's metric: serialize + pool achieved HBM GB/s (algorithmic bytes of SURVEY 8d:
     # 128 B / Gaussian for the 4-order serialization, N (28 + C e) + M (148 + 4 C) for a pooling level)
-    sp = [table[k] for k in ("ss_serialize", "ss_pool_index", "ss_segment_reduce") if k in table]
+    sp = [table[k] for k in ("ss_serialize", "ss_pool_index", "ss_segment_reduce", "ss_pool_reduce") if k in table]
     serialize_pool = None
     if sp:
         sp_bytes, sp_ms = sum(r["bytes"] for r in sp), sum(r["ms"] for r in sp)
@@ -462,7 +462,7 @@ def main():
                               ms_per_step=sp_ms / prof_steps, bytes_per_step=sp_bytes / prof_steps,
                               by_kernel={k: dict(ms_per_step=table[k]["ms"] / prof_steps,
                                                  gbs=table[k]["bytes"] / (table[k]["ms"] * 1e-3) / 1e9)
-                                         for k in ("ss_serialize", "ss_pool_index", "ss_segment_reduce") if k in table},
+                                         for k in ("ss_serialize", "ss_pool_index", "ss_segment_reduce", "ss_pool_reduce") if k in table},
                               note="device time of the serialization + the three pooling levels of the benchmark chunk")
 
     # ---- parity of the benchmarked configuration + the CPU baseline (one oracle forward on the same chunk)

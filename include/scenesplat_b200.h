@@ -91,6 +91,13 @@ int ss_segment_reduce(const void* src, int src_is_bf16, const int64_t* order, co
                       const int64_t* m_dev, int64_t m, int channels, int reduce, const float* scale, const float* shift,
                       int act, void* out, int out_is_bf16, void* stream);
 
+/* One launch for what SerializedPooling does after the index build (point_transformer_v3m1_base.py:400-404):
+ * out = segment_csr(src[order], seg_start, reduce) (+ folded-BN affine, GELU) AND coord_out =
+ * segment_csr(coord[order], seg_start, "mean") for the fp32 [n,3] coordinates, over the same segments. */
+int ss_pool_reduce(const void* src, int src_is_bf16, const float* coord, const int64_t* order, const int64_t* seg_start,
+                   int64_t m, int channels, int reduce, const float* scale, const float* shift, int act, void* out,
+                   int out_is_bf16, float* coord_out, void* stream);
+
 /* out[i,:] = f_a(a[i,:]) + f_b(b[cluster[i],:]); f = optional affine + activation.  out_a (nullable)
  * receives f_a(a) alone (what the reference's stale sparse_conv_feat holds after unpooling).
  * out_flags: bit 0 = out is bf16 (else fp32), bit 1 = out_a is bf16 even when out is fp32. */

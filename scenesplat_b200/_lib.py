@@ -28,6 +28,7 @@ SIGNATURES = {
     "ss_pool_index": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                            _vp, _sz, _vp]),
     "ss_segment_reduce": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    "ss_pool_reduce": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     "ss_unpool_gather_add": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "ss_kmap_workspace_bytes": (_sz, [_i64, _i]),
     "ss_kmap_build": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

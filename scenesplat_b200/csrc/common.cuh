@@ -191,6 +191,125 @@ __device__ __forceinline__ uint64_t hilbert_key(uint32_t x, uint32_t y, uint32_t
   return h;
 }
 
+// 32-bit forms for depth <= 10 (30-bit codes): the same bit patterns with a third of the instructions.
+__device__ __forceinline__ uint32_t spread3_10(uint32_t x) {  // 10 low bits -> every third bit
+  x &= 0x3ffu;
+  x = (x | (x << 16)) & 0x030000ffu;
+  x = (x | (x << 8)) & 0x0300f00fu;
+  x = (x | (x << 4)) & 0x030c30c3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+
+__device__ __forceinline__ uint32_t z_key32(uint32_t x, uint32_t y, uint32_t z, int depth) {
+  const uint32_t m = (1u << depth) - 1u;
+  return (spread3_10(x & m) << 2) | (spread3_10(y & m) << 1) | spread3_10(z & m);
+}
+
+__device__ __forceinline__ uint32_t hilbert_key32(uint32_t x, uint32_t y, uint32_t z, int depth) {
+  const uint32_t m = (1u << depth) - 1u;
+  uint32_t X0 = x & m, X1 = y & m, X2 = z & m;
+  for (uint32_t Q = 1u << (depth - 1); Q >= 1u; Q >>= 1) {
+    const uint32_t P = Q - 1u;
+    if (X0 & Q) X0 ^= P;
+    if (X1 & Q) {
+      X0 ^= P;
+    } else {
+      const uint32_t t = (X0 ^ X1) & P;
+      X0 ^= t;
+      X1 ^= t;
+    }
+    if (X2 & Q) {
+      X0 ^= P;
+    } else {
+      const uint32_t t = (X0 ^ X2) & P;
+      X0 ^= t;
+      X2 ^= t;
+    }
+  }
+  uint32_t h = (spread3_10(X0) << 2) | (spread3_10(X1) << 1) | spread3_10(X2);
+  h ^= h >> 1;
+  h ^= h >> 2;
+  h ^= h >> 4;
+  h ^= h >> 8;
+  h ^= h >> 16;
+  return h;
+}
+
+// The same Hilbert encoder as an MSB-first finite-state machine over the octants of the z-order key (three key bits per
+// level in, three out): state = the signed permutation the earlier levels of Skilling's transpose have accumulated on
+// the lower bits + the running parity of the Gray->binary prefix XOR.  ~7 instructions per level instead of ~25 + the
+// interleave + the XOR cascade.  hilbert(x, y, z) = fsm(z_key(x, y, z)); hilbert-trans = fsm(z_key(y, x, z)).
+// Table derived from, and verified against, the pinned restatement of hilbert.py by tools/gen_hilbert_fsm.py.
+// 48 states x 8 octants, entry = next_state << 3 | output bits; generated by tools/gen_hilbert_fsm.py
+constexpr int kHilbertStates = 48;
+static __device__ const uint16_t kHilbertFsm[kHilbertStates * 8] = {
+    8, 17, 27, 2, 39, 46, 52, 61,
+    64, 79, 81, 94, 99, 108, 10, 117,
+    48, 57, 127, 134, 139, 106, 12, 21,
+    150, 153, 29, 162, 87, 88, 172, 59,
+    180, 187, 37, 194, 207, 208, 222, 225,
+    236, 189, 35, 42, 31, 6, 240, 249,
+    216, 231, 259, 4, 265, 278, 50, 285,
+    8, 17, 27, 2, 39, 46, 52, 61,
+    0, 291, 255, 220, 281, 66, 302, 269,
+    308, 263, 227, 312, 77, 54, 274, 121,
+    104, 203, 113, 218, 191, 68, 198, 85,
+    212, 103, 229, 14, 75, 176, 90, 33,
+    174, 287, 321, 296, 101, 332, 338, 115,
+    48, 57, 127, 134, 139, 106, 12, 21,
+    64, 79, 81, 94, 99, 108, 10, 117,
+    316, 251, 295, 304, 125, 298, 70, 73,
+    244, 253, 143, 110, 123, 130, 232, 185,
+    350, 353, 271, 272, 141, 330, 340, 19,
+    166, 205, 361, 146, 63, 348, 128, 83,
+    210, 25, 157, 246, 355, 168, 92, 327,
+    150, 153, 29, 162, 87, 88, 172, 59,
+    342, 119, 261, 164, 369, 192, 170, 283,
+    178, 379, 373, 196, 257, 160, 318, 367,
+    236, 189, 35, 42, 31, 6, 240, 249,
+    180, 187, 37, 194, 207, 208, 222, 225,
+    166, 205, 361, 146, 63, 348, 128, 83,
+    210, 25, 157, 246, 355, 168, 92, 327,
+    104, 203, 113, 218, 191, 68, 198, 85,
+    212, 103, 229, 14, 75, 176, 90, 33,
+    234, 381, 371, 44, 289, 310, 144, 159,
+    242, 365, 201, 214, 323, 132, 344, 359,
+    244, 253, 143, 110, 123, 130, 232, 185,
+    342, 119, 261, 164, 369, 192, 170, 283,
+    0, 291, 255, 220, 281, 66, 302, 269,
+    308, 263, 227, 312, 77, 54, 274, 121,
+    216, 231, 259, 4, 265, 278, 50, 285,
+    334, 293, 23, 148, 377, 346, 40, 267,
+    316, 251, 295, 304, 125, 298, 70, 73,
+    306, 137, 155, 336, 357, 238, 276, 375,
+    314, 363, 97, 328, 325, 300, 182, 383,
+    314, 363, 97, 328, 325, 300, 182, 383,
+    350, 353, 271, 272, 141, 330, 340, 19,
+    174, 287, 321, 296, 101, 332, 338, 115,
+    334, 293, 23, 148, 377, 346, 40, 267,
+    306, 137, 155, 336, 357, 238, 276, 375,
+    242, 365, 201, 214, 323, 132, 344, 359,
+    178, 379, 373, 196, 257, 160, 318, 367,
+    234, 381, 371, 44, 289, 310, 144, 159,
+};
+
+// Copies the table to shared memory (caller synchronises).  `s_fsm` needs kHilbertStates * 8 entries.
+__device__ __forceinline__ void hilbert_fsm_load(uint16_t* s_fsm) {
+  for (int i = threadIdx.x; i < kHilbertStates * 8; i += blockDim.x) s_fsm[i] = kHilbertFsm[i];
+}
+
+template <typename KeyT>  // uint32_t for depth <= 10, uint64_t otherwise
+__device__ __forceinline__ KeyT hilbert_from_zkey(KeyT zk, int depth, const uint16_t* __restrict__ s_fsm) {
+  uint32_t e = 0;
+  KeyT h = 0;
+  for (int sh = 3 * (depth - 1); sh >= 0; sh -= 3) {
+    e = s_fsm[(e & 0xfff8u) | ((uint32_t)(zk >> sh) & 7u)];
+    h = (h << 3) | (KeyT)(e & 7u);
+  }
+  return h;
+}
+
 // order ids: 0 = z, 1 = z-trans, 2 = hilbert, 3 = hilbert-trans (reference serialization/default.py:8-24)
 __device__ __forceinline__ uint64_t sfc_key(int order_id, uint32_t x, uint32_t y, uint32_t z, int depth) {
   switch (order_id) {
@@ -198,6 +317,15 @@ __device__ __forceinline__ uint64_t sfc_key(int order_id, uint32_t x, uint32_t y
     case 1: return z_key(y, x, z, depth);
     case 2: return hilbert_key(x, y, z, depth);
     default: return hilbert_key(y, x, z, depth);
+  }
+}
+
+__device__ __forceinline__ uint32_t sfc_key32(int order_id, uint32_t x, uint32_t y, uint32_t z, int depth) {  // depth <= 10
+  switch (order_id) {
+    case 0: return z_key32(x, y, z, depth);
+    case 1: return z_key32(y, x, z, depth);
+    case 2: return hilbert_key32(x, y, z, depth);
+    default: return hilbert_key32(y, x, z, depth);
   }
 }
 

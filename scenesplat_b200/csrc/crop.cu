@@ -10,23 +10,32 @@
 
 namespace ss {
 
-__global__ void __launch_bounds__(256)
+constexpr int kCropBits = 8;  // 32-bit keys: 4 passes of 8 bits (make_radix_plan)
+constexpr int kCropThreads = 256;
+__global__ void __launch_bounds__(kCropThreads)
 sphere_key_kernel(const float* __restrict__ coord, int64_t n, float cx, float cy, float cz, uint64_t* __restrict__ key,
-                  uint32_t* __restrict__ ghist, int passes) {
-  extern __shared__ uint32_t s_hist[];  // [passes][256]
-  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) s_hist[i] = 0u;
+                  uint32_t* __restrict__ ghist, void* status, size_t status_bytes) {
+  constexpr int BINS = 1 << kCropBits;
+  __shared__ uint32_t s_hist[BINS];  // first-digit histogram (shared-memory atomics)
+  radix_zero_status(status, status_bytes);
+  for (int i = threadIdx.x; i < BINS; i += blockDim.x) s_hist[i] = 0u;
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float dx = __fsub_rn(coord[3 * i], cx), dy = __fsub_rn(coord[3 * i + 1], cy), dz = __fsub_rn(coord[3 * i + 2], cz);
-    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    const uint64_t k = (uint64_t)__float_as_uint(d2);
-    key[i] = k;
-    for (int ps = 0; ps < passes; ++ps) atomicAdd(&s_hist[ps * kRadix + (int)((k >> (ps * kRadixBits)) & (kRadix - 1))], 1u);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    const bool ok = i < n;
+    uint64_t k = 0;
+    if (ok) {
+      const float dx = __fsub_rn(coord[3 * i], cx), dy = __fsub_rn(coord[3 * i + 1], cy), dz = __fsub_rn(coord[3 * i + 2], cz);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      k = (uint64_t)__float_as_uint(d2);
+      key[i] = k;
+    }
+    if (ok) atomicAdd(&s_hist[(uint32_t)k & (BINS - 1)], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
-    const uint32_t c = s_hist[i];
-    if (c) atomicAdd(&ghist[i], c);
+  for (int d = threadIdx.x; d < BINS; d += blockDim.x) {
+    const uint32_t c = s_hist[d];
+    if (c) atomicAdd(&ghist[d], c);
   }
 }
 
@@ -64,10 +73,12 @@ int ss_sphere_crop_order(const float* coord, int64_t n, const float* center3, in
   if (workspace_bytes < p.total) return SS_BAD_ARGS;
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   uint64_t* key = (uint64_t*)(ws + p.off_key);
-  SS_CUDA(cudaMemsetAsync(ws + p.radix.off_hist, 0, p.radix.zero_bytes, stream));
-  const int blocks = (int)ss::imin64(ss::ceil_div64(n, 256), 8 * ss::kNumSMs);
-  ss::sphere_key_kernel<<<blocks, 256, p.radix.passes * ss::kRadix * 4, stream>>>(
-      coord, n, center3[0], center3[1], center3[2], key, (uint32_t*)(ws + p.radix.off_hist), p.radix.passes);
+  if (p.radix.bits != ss::kCropBits) return SS_BAD_ARGS;
+  SS_CUDA(cudaMemsetAsync(ws + p.radix.off_hist, 0, p.radix.small_zero_bytes, stream));
+  const int blocks = (int)ss::imin64(ss::ceil_div64(n, ss::kCropThreads), 2 * ss::kNumSMs);
+  ss::sphere_key_kernel<<<blocks, ss::kCropThreads, 0, stream>>>(coord, n, center3[0], center3[1], center3[2], key,
+                                                                 (uint32_t*)(ws + p.radix.off_hist),
+                                                                 ws + p.radix.off_status, p.radix.status_bytes);
   SS_CHECK_LAUNCH();
   return ss::radix_sort_run(p.radix, ws, key, ss::kFinalPairs, order, nullptr, dist_bits_sorted, stream);
 }

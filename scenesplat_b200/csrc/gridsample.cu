@@ -49,36 +49,45 @@ __global__ void gs_init_minmax(long long* mn, long long* mx) {
   }
 }
 
-// key = hash(voxel - min); also the digit histograms for the 8 radix passes.
-__global__ void __launch_bounds__(256)
+// key = hash(voxel - min); also the histogram of the first radix digit (warp-private counters filled by ballot matching;
+// the sort passes count the later digits themselves) and the clear of the sort's look-back status words.
+constexpr int kGsBits = 10;  // 64-bit keys: 7 passes of 10 bits (make_radix_plan)
+constexpr int kGsThreads = 256;
+__global__ void __launch_bounds__(kGsThreads)
 gs_hash_kernel(const float* __restrict__ coord, int64_t n, double grid_size, const long long* __restrict__ mn,
                const long long* __restrict__ mx, int hash_type, uint64_t* __restrict__ key, uint32_t* __restrict__ ghist,
-               int passes) {
-  extern __shared__ uint32_t s_hist[];
-  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) s_hist[i] = 0u;
+               void* status, size_t status_bytes) {
+  constexpr int BINS = 1 << kGsBits;
+  __shared__ uint32_t s_hist[BINS];  // first-digit histogram (shared-memory atomics)
+  radix_zero_status(status, status_bytes);
+  for (int i = threadIdx.x; i < BINS; i += blockDim.x) s_hist[i] = 0u;
   __syncthreads();
   const long long m0 = mn[0], m1 = mn[1], m2 = mn[2];
   const unsigned long long e1 = (unsigned long long)(mx[1] - m1) + 1ull, e2 = (unsigned long long)(mx[2] - m2) + 1ull;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned long long g0 = (unsigned long long)(voxel_of(coord[i * 3 + 0], grid_size) - m0);
-    const unsigned long long g1 = (unsigned long long)(voxel_of(coord[i * 3 + 1], grid_size) - m1);
-    const unsigned long long g2 = (unsigned long long)(voxel_of(coord[i * 3 + 2], grid_size) - m2);
-    unsigned long long h;
-    if (hash_type == 0) {  // "fnv" as written in the reference: multiply, then xor the whole coordinate
-      h = 14695981039346656037ull;
-      h *= 1099511628211ull; h ^= g0;
-      h *= 1099511628211ull; h ^= g1;
-      h *= 1099511628211ull; h ^= g2;
-    } else {  // ravel
-      h = (g0 * e1 + g1) * e2 + g2;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    const bool ok = i < n;
+    unsigned long long h = 0;
+    if (ok) {
+      const unsigned long long g0 = (unsigned long long)(voxel_of(coord[i * 3 + 0], grid_size) - m0);
+      const unsigned long long g1 = (unsigned long long)(voxel_of(coord[i * 3 + 1], grid_size) - m1);
+      const unsigned long long g2 = (unsigned long long)(voxel_of(coord[i * 3 + 2], grid_size) - m2);
+      if (hash_type == 0) {  // "fnv" as written in the reference: multiply, then xor the whole coordinate
+        h = 14695981039346656037ull;
+        h *= 1099511628211ull; h ^= g0;
+        h *= 1099511628211ull; h ^= g1;
+        h *= 1099511628211ull; h ^= g2;
+      } else {  // ravel
+        h = (g0 * e1 + g1) * e2 + g2;
+      }
+      key[i] = h;
     }
-    key[i] = h;
-    for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * kRadix + (int)((h >> (p * kRadixBits)) & (kRadix - 1))], 1u);
+    if (ok) atomicAdd(&s_hist[(uint32_t)h & (BINS - 1)], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
-    const uint32_t c = s_hist[i];
-    if (c) atomicAdd(&ghist[i], c);
+  for (int d = threadIdx.x; d < BINS; d += blockDim.x) {
+    const uint32_t c = s_hist[d];
+    if (c) atomicAdd(&ghist[d], c);
   }
 }
 
@@ -93,11 +102,8 @@ struct GsRuns {
     inverse[idx_sort[j]] = (int64_t)run;
     if (is_head) start[run] = j;
   }
+  __device__ void finish(int, uint32_t total) const { start[total] = n; }
 };
-
-__global__ void gs_close_start(int64_t* start, const int64_t* m, int64_t n) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) start[*m] = n;
-}
 
 __global__ void __launch_bounds__(256)
 gs_select_kernel(const float* __restrict__ coord, double grid_size, const long long* __restrict__ mn,
@@ -176,23 +182,23 @@ int ss_gridsample_index(const float* coord, int64_t n, double grid_size, int has
   long long* mx = mn + 4;
   uint64_t* key = (uint64_t*)(ws + p.off_key);
   uint64_t* key_sorted = (uint64_t*)(ws + p.off_keysorted);
-  SS_CUDA(cudaMemsetAsync(ws + p.radix.off_hist, 0, p.radix.zero_bytes, stream));
+  if (p.radix.bits != ss::kGsBits) return SS_BAD_ARGS;
+  SS_CUDA(cudaMemsetAsync(ws + p.radix.off_hist, 0, p.radix.small_zero_bytes, stream));
   ss::gs_init_minmax<<<1, 32, 0, stream>>>(mn, mx);
   SS_CHECK_LAUNCH();
   const int blocks = (int)ss::imin64(ss::ceil_div64(n, 256), 8 * ss::kNumSMs);
   ss::gs_minmax_kernel<<<blocks, 256, 0, stream>>>(coord, n, grid_size, mn, mx);
   SS_CHECK_LAUNCH();
-  ss::gs_hash_kernel<<<blocks, 256, p.radix.passes * ss::kRadix * 4, stream>>>(
-      coord, n, grid_size, mn, mx, hash_type, key, (uint32_t*)(ws + p.radix.off_hist), p.radix.passes);
+  ss::gs_hash_kernel<<<(int)ss::imin64(blocks, 2 * ss::kNumSMs), ss::kGsThreads, 0, stream>>>(
+      coord, n, grid_size, mn, mx, hash_type, key, (uint32_t*)(ws + p.radix.off_hist), ws + p.radix.off_status,
+      p.radix.status_bytes);
   SS_CHECK_LAUNCH();
   int rc = ss::radix_sort_run(p.radix, ws, key, ss::kFinalPairs, idx_sort, nullptr, key_sorted, stream);
   if (rc) return rc;
   ss::GsRuns f{key_sorted, idx_sort, inverse, start, n};
   rc = ss::runs_launch(f, n, ws + p.off_runs, m_dev, stream);
   if (rc) return rc;
-  ss::gs_close_start<<<1, 32, 0, stream>>>(start, m_dev, n);
   SS_CUDA(cudaMemcpyAsync(min_coord_dev, mn, 24, cudaMemcpyDeviceToDevice, stream));
-  SS_CHECK_LAUNCH();
   return SS_OK;
 }
 

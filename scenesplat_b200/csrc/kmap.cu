@@ -96,6 +96,7 @@ struct PairRuns {
       ypos[(size_t)t * n + p] = -1;
     }
   }
+  __device__ void finish(int, uint32_t) const {}
 };
 
 }  // namespace ss

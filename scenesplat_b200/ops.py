@@ -158,6 +158,19 @@ def segment_reduce(src, order_row, seg_start, reduce="mean", scale=None, shift=N
     return out
 
 
+def pool_reduce(src, coord, order_row, seg_start, reduce="mean", scale=None, shift=None, act=0, out_dtype=None):
+    """segment_reduce of the projected features and the "mean" of the fp32 coordinates over the same segments, one launch."""
+    src, coord = src.contiguous(), coord.contiguous()
+    m = seg_start.shape[0] - 1
+    c = src.shape[1]
+    out = torch.empty((m, c), dtype=out_dtype or src.dtype, device=src.device)
+    coord_out = torch.empty((m, 3), dtype=torch.float32, device=src.device)
+    L.call("ss_pool_reduce", L.ptr(src), _isbf(src), L.ptr(coord), L.ptr(order_row), L.ptr(seg_start), m, c,
+           _REDUCE[reduce], L.ptr(scale), L.ptr(shift), act, L.ptr(out), _isbf(out), L.ptr(coord_out), L.stream(),
+           meta=dict(bytes=src.shape[0] * (8.0 + c * src.element_size() + 12.0) + m * (8.0 + c * out.element_size() + 12.0)))
+    return out, coord_out
+
+
 def unpool_gather_add(a, b, cluster, scale_a=None, shift_a=None, scale_b=None, shift_b=None, act=0, out_dtype=None,
                       want_a=False, a_dtype=None):
     a, b = a.contiguous(), b.contiguous()

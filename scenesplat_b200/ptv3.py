@@ -384,9 +384,8 @@ class SerializedPooling(PointModule):
         fuse = (bn is not None or getattr(self, "norm", None) is None) and (gelu or act is None)
         proj = linear_bf16(self.proj, _bf16_of(point, point.feat))
         scale, shift = bn_fold(bn) if (fuse and bn is not None) else (None, None)
-        feat = ops.segment_reduce(proj, order0, ix["seg_start"], self.reduce, scale, shift, 1 if (fuse and gelu) else 0,
-                                  out_dtype=torch.float32)
-        coord = ops.segment_reduce(point.coord.float(), order0, ix["seg_start"], "mean")
+        feat, coord = ops.pool_reduce(proj, point.coord.float(), order0, ix["seg_start"], self.reduce, scale, shift,
+                                      1 if (fuse and gelu) else 0, out_dtype=torch.float32)
         n_batch = point.offset.numel()
         offset = torch.searchsorted(ix["batch"], torch.arange(n_batch, device=feat.device), right=True)
         names = point.serialized_order_names
