@@ -250,6 +250,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip train_step / zero_shot_scene / sweep / library bars")
     ap.add_argument("--n-raw", type=int, default=N_RAW)
     ap.add_argument("--no-pipeline", action="store_true", help="one chunk at a time (index phase not overlapped)")
+    ap.add_argument("--conv-split", action="store_true",
+                    help="A/B: xCPE conv as gather-GEMM + gather-sum kernels instead of the single fused launch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -257,6 +259,9 @@ def main():
 
     import torch.distributed as dist
     from scenesplat_b200 import _lib as L
+    if args.conv_split:
+        from scenesplat_b200 import ops as _ops
+        _ops.FUSED_CONV_MIN_C = 1 << 30
     import scenesplat_b200 as S
 
     rank = int(os.environ.get("RANK", "0"))

@@ -119,9 +119,13 @@ int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* bat
 
 /* Compacted pair lists for the gather-GEMM path: tap t owns rows [tap_base[t], tap_base[t] + count[t])
  * of the product buffer; pair_in [p_pad] = input row of every product row, ypos [k^3, n] = product row
- * of (tap, output voxel) or -1. */
+ * of (tap, output voxel) or -1; ypos_rank (nullable, k = 3) [n, 32] = the same positions indexed by the output's RANK
+ * along order_row (columns >= 27 are -1): what the fused conv's reducer warps read, one 128-byte line per output;
+ * tile_first_rank (nullable; tap bases multiples of 256) [p_pad / 256] = rank of the first output of every 256-row tile
+ * of the product buffer (the fused conv produces the tiles in that order). */
 int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k, const int64_t* tap_base_dev,
-                  int64_t p_pad, int32_t* pair_in, int32_t* ypos, void* workspace, size_t workspace_bytes, void* stream);
+                  int64_t p_pad, int32_t* pair_in, int32_t* ypos, int32_t* ypos_rank, int32_t* tile_first_rank,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* SIMT fp32-accumulate conv: out[p,co] = bias[co] + sum_t sum_ci wt[t][ci][co] * in[nbr[t][p]][ci],
  * then optional affine (folded BN) + activation.  wt is the [k^3, cin, cout] fp32 re-layout of the
@@ -160,6 +164,21 @@ int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float*
 int ss_subm_conv_reduce_add_ln(const void* prod_bf16, const int32_t* ypos, const float* bias, const float* res, const float* g0,
                                const float* b0, const float* g1, const float* b1, float eps, int64_t n, int k3, int channels,
                                float* res_out, void* norm_out_bf16, void* stream);
+
+/* The xCPE conv of a Block in ONE launch (cout >= 256, k3 <= 32): ss_subm_conv_gemm_pair + ss_subm_conv_reduce_add_ln,
+ * bit-identical to that pair of calls.  Twelve reducer warps per CTA walk the output voxels along `order_row` (the
+ * serialized order the pair lists were built along), wait on per-tile completion counters and sum the product rows
+ * while they are still in L2; the GEMM takes the 256-row product tiles in `tile_order` (a permutation of the p_pad / 256
+ * tiles: by the rank of each tile's first output, ops.kmap_pairs; tile_pos is its inverse) and never runs more than
+ * ~48 MB of products ahead of the tiles the reducers have asked for, so the products are read back from L2.  prod_bf16
+ * [p_pad, cout] and tile_flags [p_pad / 256 + 2] are scratch; ypos_rank [n, 32] from ss_kmap_pairs.  Replaces spconv.SubMConv3d + Linear + LayerNorm + residual +
+ * LayerNorm of point_transformer_v3m1_base.py:277-287,318-326. */
+int ss_subm_conv_fused_add_ln(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
+                              const int32_t* tile_order, const int32_t* tile_pos, int64_t p_pad, int k3, int cin, int cout,
+                              void* prod_bf16, int32_t* tile_flags, const int64_t* order_row, const int32_t* ypos_rank,
+                              const float* bias,
+                              const float* res, const float* g0, const float* b0, const float* g1, const float* b1, float eps,
+                              int64_t n, float* res_out, void* norm_out_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SerializedAttention (point_transformer_v3m1_base.py:114-222). */

@@ -9,6 +9,7 @@
 // (2) conv_reduce_kernel: out[p, :] = bias + sum_t prod[ypos[t][p], :], the HBM-bound second stage of the xCPE conv
 //     (first stage: the gather-GEMMs of conv_gemm2.cu / conv_gemm3.cu).
 #include "tc_common.cuh"
+#include "conv_reduce.cuh"
 #include "../../include/scenesplat_b200.h"
 
 namespace ss {
@@ -171,7 +172,8 @@ head_gemm_kernel(const __nv_bfloat16* __restrict__ X, const __grid_constant__ CU
 
 // out[p, :] = bias + sum_t prod[ypos[t][p], :]; one warp per output voxel, 16-byte (8 x bf16) lanes, J x 256
 // channels per pass.  The voxel's k3 product-row positions are fetched with ONE load (lane = tap), the active ones
-// are walked in ascending tap order (fixed summation order) four at a time so four row loads are in flight per lane.
+// are walked in ascending tap order (fixed summation order) four at a time so four row loads are in flight per lane
+// (conv_reduce.cuh).
 template <typename TO, int J>
 __global__ void __launch_bounds__(256)
 conv_reduce_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __restrict__ ypos,
@@ -181,47 +183,10 @@ conv_reduce_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __rest
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t p = warp0; p < n; p += nwarp) {
     float acc[J][8];
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int c0 = j * 256 + lane * 8;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc[j][u] = (bias && c0 < cout) ? bias[c0 + u] : 0.f;
-    }
+    conv_acc_init<J>(bias, lane, cout, acc);
     for (int t0 = 0; t0 < k3; t0 += 32) {
       const int32_t mypos = (t0 + lane < k3) ? ypos[(size_t)(t0 + lane) * n + p] : -1;
-      uint32_t m = __ballot_sync(0xffffffffu, mypos >= 0);
-      while (m) {
-        int32_t pos[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int t = m ? __ffs(m) - 1 : 0;
-          pos[q] = m ? __shfl_sync(0xffffffffu, mypos, t) : -1;
-          m &= m - 1;  // (0 stays 0)
-        }
-        uint4 v[4][J];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int j = 0; j < J; ++j) {
-            const int c0 = j * 256 + lane * 8;
-            v[q][j] = make_uint4(0u, 0u, 0u, 0u);
-            if (pos[q] >= 0 && c0 < cout) v[q][j] = *reinterpret_cast<const uint4*>(prod + (size_t)pos[q] * cout + c0);
-          }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (pos[q] < 0) continue;  // warp-uniform; (adding the zero vector would turn a -0 sum into +0)
-#pragma unroll
-          for (int j = 0; j < J; ++j) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[q][j]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 f = __bfloat1622float2(h[u]);
-              acc[j][2 * u] += f.x;
-              acc[j][2 * u + 1] += f.y;
-            }
-          }
-        }
-      }
+      conv_gather_sum<J, false>(prod, mypos, lane, cout, acc);
     }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
@@ -247,7 +212,7 @@ conv_reduce_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __rest
 // Linear folded into the taps): z = bias + sum_t prod[ypos[t][p], :] stays in registers (fp32, never rounded to bf16),
 // y = res + LN0(z) is written as the new fp32 residual stream and LN1(y) as the bf16 operand of the qkv GEMM.  One warp
 // per voxel, as in conv_reduce_kernel; the two LayerNorm reductions are warp shuffles.  Saves the write + read of z and
-// one launch per Block.
+// one launch per Block.  (For C >= 256 the same body runs inside the gather-GEMM itself: conv_gemm3.cu.)
 template <int J>
 __global__ void __launch_bounds__(256)
 conv_reduce_add_ln_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __restrict__ ypos,
@@ -258,128 +223,14 @@ conv_reduce_add_ln_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t*
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const float invC = 1.f / (float)C;
-  auto warp_sum = [](float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  };
   for (int64_t p = warp0; p < n; p += nwarp) {
     float acc[J][8];
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int c0 = j * 256 + lane * 8;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc[j][u] = (bias && c0 < C) ? bias[c0 + u] : 0.f;
-    }
+    conv_acc_init<J>(bias, lane, C, acc);
     for (int t0 = 0; t0 < k3; t0 += 32) {
       const int32_t mypos = (t0 + lane < k3) ? ypos[(size_t)(t0 + lane) * n + p] : -1;
-      uint32_t m = __ballot_sync(0xffffffffu, mypos >= 0);
-      while (m) {
-        int32_t pos[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int t = m ? __ffs(m) - 1 : 0;
-          pos[q] = m ? __shfl_sync(0xffffffffu, mypos, t) : -1;
-          m &= m - 1;  // (0 stays 0)
-        }
-        uint4 v[4][J];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int j = 0; j < J; ++j) {
-            const int c0 = j * 256 + lane * 8;
-            v[q][j] = make_uint4(0u, 0u, 0u, 0u);
-            if (pos[q] >= 0 && c0 < C) v[q][j] = *reinterpret_cast<const uint4*>(prod + (size_t)pos[q] * C + c0);
-          }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (pos[q] < 0) continue;  // warp-uniform
-#pragma unroll
-          for (int j = 0; j < J; ++j) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[q][j]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 f = __bfloat1622float2(h[u]);
-              acc[j][2 * u] += f.x;
-              acc[j][2 * u + 1] += f.y;
-            }
-          }
-        }
-      }
+      conv_gather_sum<J, false>(prod, mypos, lane, C, acc);
     }
-    // ---- LN0(z)
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < J; ++j)
-#pragma unroll
-      for (int u = 0; u < 8; ++u) s += acc[j][u];  // lanes past C hold zeros
-    float mean = warp_sum(s) * invC;
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const bool ok = j * 256 + lane * 8 < C;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float d = ok ? acc[j][u] - mean : 0.f;
-        q += d * d;
-      }
-    }
-    float rstd = rsqrtf(warp_sum(q) * invC + eps);
-    // ---- y = res + LN0(z)
-    s = 0.f;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int c0 = j * 256 + lane * 8;
-      if (c0 < C) {
-        const float4 ga = *reinterpret_cast<const float4*>(g0 + c0), gb = *reinterpret_cast<const float4*>(g0 + c0 + 4);
-        const float4 ba = *reinterpret_cast<const float4*>(b0 + c0), bb = *reinterpret_cast<const float4*>(b0 + c0 + 4);
-        const float4 xa = *reinterpret_cast<const float4*>(res + (size_t)p * C + c0);
-        const float4 xb = *reinterpret_cast<const float4*>(res + (size_t)p * C + c0 + 4);
-        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-        const float xx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          acc[j][u] = xx[u] + ((acc[j][u] - mean) * rstd * gg[u] + bt[u]);
-          s += acc[j][u];
-        }
-        float4* o = reinterpret_cast<float4*>(res_out + (size_t)p * C + c0);
-        o[0] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-        o[1] = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
-      }
-    }
-    // ---- LN1(y) -> bf16
-    mean = warp_sum(s) * invC;
-    q = 0.f;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const bool ok = j * 256 + lane * 8 < C;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float d = ok ? acc[j][u] - mean : 0.f;
-        q += d * d;
-      }
-    }
-    rstd = rsqrtf(warp_sum(q) * invC + eps);
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int c0 = j * 256 + lane * 8;
-      if (c0 < C) {
-        const float4 ga = *reinterpret_cast<const float4*>(g1 + c0), gb = *reinterpret_cast<const float4*>(g1 + c0 + 4);
-        const float4 ba = *reinterpret_cast<const float4*>(b1 + c0), bb = *reinterpret_cast<const float4*>(b1 + c0 + 4);
-        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-        float o[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) o[u] = (acc[j][u] - mean) * rstd * gg[u] + bt[u];
-        uint4 w;
-        w.x = tc::pack_bf16(o[0], o[1]);
-        w.y = tc::pack_bf16(o[2], o[3]);
-        w.z = tc::pack_bf16(o[4], o[5]);
-        w.w = tc::pack_bf16(o[6], o[7]);
-        *reinterpret_cast<uint4*>(norm_out + (size_t)p * C + c0) = w;
-      }
-    }
+    conv_ln_res_ln_store<J>(acc, p, lane, C, invC, eps, res, g0, b0, g1, b1, res_out, norm_out);
   }
 }
 

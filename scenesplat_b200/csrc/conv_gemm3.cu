@@ -28,11 +28,19 @@
 // 15 warps per CTA: 0-7 epilogue (row quarter x column half), 8-11 A gather, 12 W producer (TMA, one lane),
 // 13 MMA issuer (leader) + TMEM allocator, 14 relay (peer).
 #include "pair_common.cuh"
+#include "conv_reduce.cuh"
 #include "../../include/scenesplat_b200.h"
 
 namespace ss {
 
 constexpr int kG3Threads = 480;
+#ifndef SS_G3_RED_WARPS
+#define SS_G3_RED_WARPS 12
+#endif
+constexpr int kG3RedWarps = SS_G3_RED_WARPS;      // reducer warps of the fused kernel (warps 16..27; warp 15 idles)
+constexpr int kG3FusedThreads = 512 + 32 * kG3RedWarps;
+// register budget per thread of the fused kernel (setmaxnreg, by warpgroup): 8 epilogue warps x 88, 4 gather warps x 48,
+// 4 producer / issuer / relay warps x 40, 12 reducer warps x 80 = 64,512 of the SM's 65,536
 constexpr int kG3BK = 64;
 constexpr int kG3SA = 7;  // A ring (gathered rows: ~3 us of latency under load, so as many bytes in flight as fit)
 constexpr int kG3SW = 4;  // W ring (TMA: a quarter of that latency)
@@ -48,10 +56,78 @@ struct Gemm3Smem {
   static constexpr int kTotal = kOffBar + 512 + 1024;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG3Threads, 1)
+// Arguments of the fused gather-sum stage (J > 0).
+struct ConvFuse {
+  const int32_t* tile_order;  // [tiles] processing order of the 256-row product tiles: by the rank of their first output
+  const int32_t* tile_pos;    // [tiles] inverse of tile_order
+  int* tile_flag;             // [tiles + 2] zeroed by the caller; += 1 per epilogue warp and item of the tile; word
+                              // `tiles + 1` is the reducers' FRONT: the furthest tile (in processing order, + 1) a reducer
+                              // has reached (posted every 16th voxel) or has had to wait for
+  int n_tiles;
+  int flag_target;            // 16 * n_slabs: all of the tile's products are in memory
+  int lag_tiles;              // the GEMM starts tile k (in processing order) only while k < front + lag_tiles
+  const int64_t* order_row;   // [n] the serialized order the pair lists were built along
+  const int32_t* ypos_rank;   // [n][32] product rows of the voxel at rank r (ss_kmap_pairs)
+  const float* bias;
+  const float* res;
+  const float* g0;
+  const float* b0;
+  const float* g1;
+  const float* b1;
+  float eps;
+  int64_t n;
+  int k3;
+  float* res_out;
+  __nv_bfloat16* norm_out;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add1(int* p) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+#ifndef SS_G3_LAG_MB
+#define SS_G3_LAG_MB 32
+#endif
+#ifndef SS_G3_SETMAXNREG
+#define SS_G3_SETMAXNREG 0
+#endif
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+#if SS_G3_SETMAXNREG
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+#endif
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+#if SS_G3_SETMAXNREG
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+#endif
+}
+
+// J = 0: products only.  J = 1..4 (= ceil(cout / 256)): FUSED gather-sum + LN + residual + LN.  Twelve more warps per CTA
+// (registers re-divided between the roles with setmaxnreg) walk the output voxels in serialized order, 32 consecutive
+// ranks per grab of a global counter (the order the pair rows of every tap follow), wait until the <= 27 product
+// tiles the voxel needs have been stored (per-tile counters, release / acquire), sum the rows and finish the Block's
+// LN(cpe) + residual + LN(norm1) (conv_reduce.cuh).  The tiles are processed in the order of their first output's rank
+// (tile_order) instead of tap by tap, so the reducers trail the GEMM front by a few tiles: the bf16 products are read
+// back from L2 instead of making a 2 x 3 GB round trip through HBM (dec0), the gathered input rows of the 27 taps of a
+// region are L2 hits, and the gather-sum pass (1.03 ms at dec0) runs under the MMAs.  GEMM roles never wait for
+// reducers and every CTA of the persistent grid is resident (1 per SM), so the waits cannot deadlock.
+template <int J>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(J > 0 ? kG3FusedThreads : kG3Threads, 1)
 gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restrict__ pair_in,
                         const __grid_constant__ CUtensorMap tmap_w, const int32_t* __restrict__ tile_tap, int cin, int cout,
-                        int n_slabs, int64_t n_items, __nv_bfloat16* __restrict__ prod) {
+                        int n_slabs, int64_t n_items, __nv_bfloat16* __restrict__ prod, const ConvFuse fz) {
+  constexpr bool FUSE = J > 0;
   using S = Gemm3Smem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -95,12 +171,27 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8 && warp < 12) {
+    if constexpr (FUSE) setmaxnreg_dec<48>();
     // ------------------------------------------------------------------ A gather: 128 threads, this CTA's 128 rows
     const int tid = threadIdx.x - 256;      // 0..127
     const int sub = tid >> 3, c = tid & 7;  // 8 lanes cover one 128-byte row segment
     int64_t g = 0;
     for (int64_t item = pair_id; item < n_items; item += n_pairs) {
-      const int64_t tile = item / n_slabs;
+      const int64_t tile = FUSE ? fz.tile_order[item / n_slabs] : item / n_slabs;
+      if constexpr (FUSE) {
+        // stay within lag_tiles of what the reducers have asked for: the products are read back while still in L2.
+        // (Every tile a reducer waits for is below its own request, so this wait cannot starve the reducers.)
+        const int k = (int)(item / n_slabs);
+        const int* front = fz.tile_flag + fz.n_tiles + 1;
+        if (lane == 0 && k >= ld_relaxed_gpu(front) + fz.lag_tiles) {
+          const uint64_t t0 = tc::global_timer_ns();
+          while (k >= ld_relaxed_gpu(front) + fz.lag_tiles) {
+            __nanosleep(500);
+            if (tc::global_timer_ns() - t0 > 4000000000ull) __trap();  // 4 s: a protocol bug must trap, never hang
+          }
+        }
+        __syncwarp();
+      }
       int32_t rows[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) rows[i] = pair_in[tile * kG3TileM + rank * 128 + i * 16 + sub];
@@ -121,13 +212,17 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
         tc::cp_async_mbar_arrive_noinc(leader ? &a_full[s] : &a_done[s]);
       }
     }
-  } else if (warp == 12) {
+  } else if (warp >= 12 && warp < 16) {
+    // W producer, MMA issuer, relay (and an idle warp in the fused kernel): one warpgroup, one register budget
+    if constexpr (FUSE) setmaxnreg_dec<40>();
+    if (warp == 12) {
     // ------------------------------------------------------------------ W producer (TMA, one lane, both CTAs)
     if (lane == 0) {
       int64_t g = 0;
       for (int64_t item = pair_id; item < n_items; item += n_pairs) {
-        const int64_t tile = item / n_slabs;
-        const int n0 = (int)(item - tile * n_slabs) * kG3BN;
+        const int64_t tidx = item / n_slabs;
+        const int64_t tile = FUSE ? fz.tile_order[tidx] : tidx;
+        const int n0 = (int)(item - tidx * n_slabs) * kG3BN;
         const int tap = tile_tap[tile];
         for (int kc = 0; kc < nk; ++kc, ++g) {
           const int s = (int)(g % kG3SW);
@@ -138,7 +233,7 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
         }
       }
     }
-  } else if (warp == 14) {
+    } else if (warp == 14) {
     // ------------------------------------------------------------------ relay (peer): "my 128 rows of the stage have landed"
     // one lane per A slot: a remote arrive has microseconds of latency, so the slots' hand-overs must overlap
     if (!leader && lane < kG3SA) {
@@ -150,7 +245,7 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
         pair::mbar_arrive_cta_relaxed(&a_full[lane], 0);
       }
     }
-  } else if (warp == 13) {
+    } else if (warp == 13) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kG3TileM, kG3BN);
@@ -179,15 +274,18 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
         pair::umma_commit_elect(&acc_full[b]);
       }
     }
+    }
   } else if (warp < 8) {
+    if constexpr (FUSE) setmaxnreg_inc<88>();
     // ------------------------------------------------------------------ epilogue warps 0..7: (row quarter, column half)
     uint8_t* stg = smem + S::kOffEpi + warp * 2048;
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int it = 0;
     for (int64_t item = pair_id; item < n_items; item += n_pairs, ++it) {
-      const int64_t tile = item / n_slabs;
-      const int n0 = (int)(item - tile * n_slabs) * kG3BN;
+      const int64_t tidx = item / n_slabs;
+      const int64_t tile = FUSE ? fz.tile_order[tidx] : tidx;
+      const int n0 = (int)(item - tidx * n_slabs) * kG3BN;
       const int b = it & 1;
       tc::mbar_wait(&acc_full[b], (uint32_t)((it >> 1) & 1));
       tc::tc_fence_after();
@@ -218,7 +316,64 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) pair::mbar_arrive_cta(&acc_empty[b], 0);
+      if (lane == 0) {
+        pair::mbar_arrive_cta(&acc_empty[b], 0);
+        if (FUSE) red_release_gpu_add1(fz.tile_flag + tile);  // this warp's share of the tile is in memory
+      }
+    }
+  } else if (FUSE && warp >= 16) {
+    if constexpr (FUSE) setmaxnreg_inc<80>();
+    // ------------------------------------------------------------------ reducers: one warp per output voxel, in rank order
+    constexpr int JJ = FUSE ? J : 1;
+    constexpr int RR = JJ >= 3 ? 2 : 4;  // product rows in flight per lane (80 registers per thread)
+    const int64_t n = fz.n;
+    const float invC = 1.f / (float)cout;
+    int* front = fz.tile_flag + fz.n_tiles + 1;
+    // Ranks w, w + W, w + 2 W, ... (W = all reducer warps of the grid): the warps move through the ranks together (the
+    // leaders are held back by the tiles the GEMM has not produced yet), so the live part of the product buffer is the GEMM's
+    // lead (lag_tiles) plus ~W outputs.  The index chain rank -> (voxel id, row of product
+    // positions) -> tile flags is fetched two / one voxel ahead, so a voxel costs the product loads, the residual load
+    // and the stores.
+    const int64_t W = (int64_t)gridDim.x * kG3RedWarps;
+    int64_t r = (int64_t)blockIdx.x * kG3RedWarps + (warp - 16);
+    int64_t p_a = r < n ? fz.order_row[r] : 0, p_b = r + W < n ? fz.order_row[r + W] : 0;
+    int32_t pos_a = r < n ? fz.ypos_rank[(size_t)r * 32 + lane] : -1;
+    int32_t pos_b = r + W < n ? fz.ypos_rank[(size_t)(r + W) * 32 + lane] : -1;
+    int flag_a = pos_a >= 0 ? ld_acquire_gpu(fz.tile_flag + (pos_a >> 8)) : 0x7fffffff;
+    for (int it = 0; r < n; r += W, ++it) {
+      const int64_t p = p_a;
+      const int32_t mypos = pos_a;
+      int flag = flag_a;
+      // prefetch: flags of the next voxel, positions / voxel id of the one after it
+      p_a = p_b;
+      pos_a = pos_b;
+      flag_a = pos_a >= 0 ? ld_acquire_gpu(fz.tile_flag + (pos_a >> 8)) : 0x7fffffff;
+      p_b = r + 2 * W < n ? fz.order_row[r + 2 * W] : 0;
+      pos_b = r + 2 * W < n ? fz.ypos_rank[(size_t)(r + 2 * W) * 32 + lane] : -1;
+      // every 16th voxel: tell the GEMM how far this warp has come (the centre tap's tile: every voxel has one), so that
+      // it keeps lag_tiles ahead of the reducers without waiting for one of them to run dry.  (Rare on purpose: same-
+      // address atomics serialise in one L2 slice at ~5 ns each; one per voxel made them the kernel's bottleneck.)
+      if ((it & 15) == 0 && lane == fz.k3 / 2 && mypos >= 0) atomicMax(front, fz.tile_pos[mypos >> 8] + 1);
+      if (flag < fz.flag_target) {  // (lanes without a pair carry INT_MAX)
+        const int t = mypos >> 8;
+        const int* f = fz.tile_flag + t;
+        if (ld_relaxed_gpu(f) < fz.flag_target) {
+          atomicMax(front, fz.tile_pos[t] + 1);  // the GEMM may be holding this tile back: let it run up to it
+          const uint64_t t0 = tc::global_timer_ns();
+          while (ld_acquire_gpu(f) < fz.flag_target) {
+            __nanosleep(200);
+            if (tc::global_timer_ns() - t0 > 4000000000ull) __trap();  // 4 s
+          }
+        }
+      }
+      // every lane has seen its tile's release counter complete with an acquire load; the warp barrier extends that to
+      // the rows of the other lanes' taps
+      __syncwarp();
+      float acc[JJ][8];
+      conv_acc_init<JJ>(fz.bias, lane, cout, acc);
+      conv_gather_sum<JJ, true, RR>(prod, mypos, lane, cout, acc);
+      conv_ln_res_ln_store<JJ>(acc, p, lane, cout, invC, fz.eps, fz.res, fz.g0, fz.b0, fz.g1, fz.b1, fz.res_out,
+                               fz.norm_out);
     }
   }
   tc::tc_fence_before();
@@ -232,6 +387,39 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
 
 }  // namespace ss
 
+namespace ss {
+
+template <int J>
+static int launch_gather_gemm_pair(const void* in_bf16, const int32_t* pair_in, const void* w_bf16, const int32_t* tile_tap,
+                                   int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, const ConvFuse& fz,
+                                   cudaStream_t stream) {
+  const int64_t tiles = p_pad / kG3TileM;
+  // W viewed as one [k3 * cout, cin] K-major matrix, boxes of 128 rows (one CTA's half of a 256-column slab); a box that
+  // runs past a tap's last column reads the next tap's rows (or zeros past the end): those columns are never stored
+  CUtensorMap tmap;
+  int rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)k3 * cout, (uint64_t)cin, 128, kG3BK);
+  if (rc) return rc;
+  auto kern = gather_gemm_pair_kernel<J>;
+  SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3Smem::kTotal));
+  const int n_slabs = (cout + kG3BN - 1) / kG3BN;
+  const int64_t n_items = tiles * n_slabs;
+  const int pairs = (int)imin64(n_items, kNumSMs / 2);
+  ConvFuse f = fz;
+  f.flag_target = 16 * n_slabs;
+  f.n_tiles = (int)tiles;
+  // ~SS_G3_LAG_MB MB of products between the GEMM front and the furthest tile asked for; never fewer tiles than keep every CTA pair
+  // two items deep
+  const int64_t lag_bytes = (int64_t)SS_G3_LAG_MB * 1024 * 1024 / (512ll * cout), lag_min = 2 * (kNumSMs / 2) / n_slabs + 8;
+  f.lag_tiles = (int)(lag_bytes > lag_min ? lag_bytes : lag_min);
+  if (J > 0) SS_CUDA(cudaMemsetAsync(f.tile_flag, 0, (size_t)(tiles + 2) * sizeof(int), stream));
+  kern<<<2 * pairs, J > 0 ? kG3FusedThreads : kG3Threads, Gemm3Smem::kTotal, stream>>>(
+      (const __nv_bfloat16*)in_bf16, pair_in, tmap, tile_tap, cin, cout, n_slabs, n_items, (__nv_bfloat16*)prod_bf16, f);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+}  // namespace ss
+
 extern "C" int ss_subm_conv_gemm_pair(const void* in_bf16, const int32_t* pair_in, const void* w_bf16,
                                       const int32_t* tile_tap, int64_t p_pad, int k3, int cin, int cout, void* prod_bf16,
                                       void* stream_) {
@@ -241,19 +429,40 @@ extern "C" int ss_subm_conv_gemm_pair(const void* in_bf16, const int32_t* pair_i
   if (p_pad == 0) return SS_OK;
   if (!in_bf16 || !pair_in || !w_bf16 || !tile_tap || !prod_bf16) return SS_BAD_ARGS;
   if (((uintptr_t)in_bf16 | (uintptr_t)w_bf16 | (uintptr_t)prod_bf16) % 16 != 0) return SS_BAD_ARGS;
-  const int64_t tiles = p_pad / ss::kG3TileM;
-  // W viewed as one [k3 * cout, cin] K-major matrix, boxes of 128 rows (one CTA's half of a 256-column slab); a box that
-  // runs past a tap's last column reads the next tap's rows (or zeros past the end): those columns are never stored
-  CUtensorMap tmap;
-  int rc = ss::make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)k3 * cout, (uint64_t)cin, 128, ss::kG3BK);
-  if (rc) return rc;
-  auto kern = ss::gather_gemm_pair_kernel;
-  SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ss::Gemm3Smem::kTotal));
-  const int n_slabs = (cout + ss::kG3BN - 1) / ss::kG3BN;
-  const int64_t n_items = tiles * n_slabs;
-  const int pairs = (int)ss::imin64(n_items, ss::kNumSMs / 2);
-  kern<<<2 * pairs, ss::kG3Threads, ss::Gemm3Smem::kTotal, stream>>>((const __nv_bfloat16*)in_bf16, pair_in, tmap, tile_tap, cin,
-                                                                     cout, n_slabs, n_items, (__nv_bfloat16*)prod_bf16);
-  SS_CHECK_LAUNCH();
-  return SS_OK;
+  return ss::launch_gather_gemm_pair<0>(in_bf16, pair_in, w_bf16, tile_tap, p_pad, k3, cin, cout, prod_bf16, ss::ConvFuse{},
+                                        stream);
+}
+
+// The xCPE conv of a Block in ONE launch: gather-GEMM + gather-sum + LN(cpe) + residual + LN(norm1)
+// (ss_subm_conv_gemm_pair followed by ss_subm_conv_reduce_add_ln, bit-identical to that pair of calls).
+// tile_order: a permutation of the p_pad / 256 product tiles (ops.kmap_pairs: by the rank of the tile's first output);
+// tile_flags: p_pad / 256 ints of scratch; order_row: the serialized order the pair lists were built along.
+extern "C" int ss_subm_conv_fused_add_ln(const void* in_bf16, const int32_t* pair_in, const void* w_bf16,
+                                         const int32_t* tile_tap, const int32_t* tile_order, const int32_t* tile_pos,
+                                         int64_t p_pad, int k3, int cin, int cout, void* prod_bf16, int32_t* tile_flags,
+                                         const int64_t* order_row, const int32_t* ypos_rank, const float* bias,
+                                         const float* res, const float* g0,
+                                         const float* b0, const float* g1, const float* b1, float eps, int64_t n,
+                                         float* res_out, void* norm_out_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (k3 < 1 || k3 > 32 || p_pad < 0 || p_pad % ss::kG3TileM != 0 || cin < 16 || cin % 16 != 0 || cout < 256 ||
+      cout % 32 != 0 || cout > 1024 || n < 0)
+    return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if (p_pad == 0) return SS_BAD_ARGS;  // every voxel has its centre tap
+  if (!in_bf16 || !pair_in || !w_bf16 || !tile_tap || !tile_order || !tile_pos || !prod_bf16 || !tile_flags || !order_row ||
+      !ypos_rank ||
+      !res || !g0 || !b0 || !g1 || !b1 || !res_out || !norm_out_bf16)
+    return SS_BAD_ARGS;
+  if (((uintptr_t)in_bf16 | (uintptr_t)w_bf16 | (uintptr_t)prod_bf16 | (uintptr_t)res | (uintptr_t)res_out |
+       (uintptr_t)norm_out_bf16 | (uintptr_t)bias | (uintptr_t)g0 | (uintptr_t)b0 | (uintptr_t)g1 | (uintptr_t)b1) % 16 != 0)
+    return SS_BAD_ARGS;
+  ss::ConvFuse f{tile_order, tile_pos, (int*)tile_flags, 0, 0, 0, order_row, ypos_rank, bias, res, g0, b0, g1, b1, eps, n, k3, res_out,
+                 (__nv_bfloat16*)norm_out_bf16};
+  switch ((cout + 255) / 256) {
+    case 1: return ss::launch_gather_gemm_pair<1>(in_bf16, pair_in, w_bf16, tile_tap, p_pad, k3, cin, cout, prod_bf16, f, stream);
+    case 2: return ss::launch_gather_gemm_pair<2>(in_bf16, pair_in, w_bf16, tile_tap, p_pad, k3, cin, cout, prod_bf16, f, stream);
+    case 3: return ss::launch_gather_gemm_pair<3>(in_bf16, pair_in, w_bf16, tile_tap, p_pad, k3, cin, cout, prod_bf16, f, stream);
+    default: return ss::launch_gather_gemm_pair<4>(in_bf16, pair_in, w_bf16, tile_tap, p_pad, k3, cin, cout, prod_bf16, f, stream);
+  }
 }

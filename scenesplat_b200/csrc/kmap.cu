@@ -84,6 +84,8 @@ struct PairRuns {
   int64_t n;
   int32_t* pair_in;   // [P_pad]  input row of every Y row
   int32_t* ypos;      // [k3][n]  Y row of (tap, output point) or -1
+  int32_t* ypos_rank; // [n][32] (nullable, k3 <= 32) the same by RANK j along `order`: one 128-byte line per output
+  int32_t* tile_first_rank;  // [P_pad / 256] (nullable) rank j of the first output of every 256-row product tile
   // "head" = pair is active: rank among active pairs of the tap = exclusive count of heads before j
   __device__ bool head(int t, int64_t j) const { return nbr[(size_t)t * n + order[j]] >= 0; }
   __device__ void emit(int t, int64_t j, uint32_t run, bool is_head) const {
@@ -92,8 +94,11 @@ struct PairRuns {
       const int64_t pos = tap_base[t] + (int64_t)run;
       pair_in[pos] = nbr[(size_t)t * n + p];
       ypos[(size_t)t * n + p] = (int32_t)pos;
+      if (ypos_rank) ypos_rank[j * 32 + t] = (int32_t)pos;
+      if (tile_first_rank && (run & 255u) == 0u) tile_first_rank[pos >> 8] = (int32_t)j;  // tap bases are multiples of 256
     } else {
       ypos[(size_t)t * n + p] = -1;
+      if (ypos_rank) ypos_rank[j * 32 + t] = -1;
     }
   }
   __device__ void finish(int, uint32_t) const {}
@@ -142,18 +147,21 @@ int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* bat
 }
 
 int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k, const int64_t* tap_base_dev,
-                  int64_t p_pad, int32_t* pair_in, int32_t* ypos, void* workspace, size_t workspace_bytes,
-                  void* stream_) {
+                  int64_t p_pad, int32_t* pair_in, int32_t* ypos, int32_t* ypos_rank, int32_t* tile_first_rank,
+                  void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n < 0 || (k != 3 && k != 5) || p_pad < 0) return SS_BAD_ARGS;
   if (n == 0) return SS_OK;
   if (!nbr || !order_row || !tap_base_dev || !pair_in || !ypos || !workspace) return SS_BAD_ARGS;
+  if ((ypos_rank && k != 3) || (tile_first_rank && p_pad % 256 != 0)) return SS_BAD_ARGS;
+  // columns 27..31 of the rank-major table stay -1
+  if (ypos_rank) SS_CUDA(cudaMemsetAsync(ypos_rank, 0xff, (size_t)n * 32 * 4, stream));
   // padding rows of every tap segment gather row 0 (their products are never read back)
   SS_CUDA(cudaMemsetAsync(pair_in, 0, (size_t)p_pad * 4, stream));
   if (workspace_bytes < ss_kmap_workspace_bytes(n, k) - 512) return SS_BAD_ARGS;
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   ws += ss::align_up((size_t)n * 8, 256);
-  ss::PairRuns f{nbr, order_row, tap_base_dev, n, pair_in, ypos};
+  ss::PairRuns f{nbr, order_row, tap_base_dev, n, pair_in, ypos, ypos_rank, tile_first_rank};
   return ss::runs_launch(f, n, ws, nullptr, stream, k * k * k);
 }
 

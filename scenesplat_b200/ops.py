@@ -214,11 +214,14 @@ def upload(values, dtype, device):
 
 
 CONV_TILE = 256  # rows per gather-GEMM tile (one CTA pair = 2 x 128, or one CTA with two accumulators)
+FUSED_CONV_MIN_C = 512  # from this width on the xCPE conv + gather-sum + LN + residual + LN is ONE launch
 
 
 def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = None):
     """Pair lists for the gather-GEMM conv.  -> dict(pair_in [p_pad] i32, ypos [k^3, n] i32, tile_tap [p_pad/tile] i32,
-    p_pad, pairs, tile).  Every tap's segment is padded to a multiple of `tile` rows."""
+    p_pad, pairs, tile, ...).  Every tap's segment is padded to a multiple of `tile` rows.  For the fused conv
+    (ss_subm_conv_fused_add_ln; k = 3, 256-row tiles) also: ypos_rank, tile_order (the tiles sorted by the rank along
+    `order_row` of their first output, as ss_kmap_pairs reports it), its inverse tile_pos, tile_flags (scratch), order_row."""
     tile = tile or CONV_TILE
     k3, n = nbr.shape
     dev = nbr.device
@@ -232,11 +235,21 @@ def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = None):
     base_dev = upload(base, torch.int64, dev)
     pair_in = torch.empty(max(p_pad, 1), dtype=torch.int32, device=dev)
     ypos = torch.empty((k3, n), dtype=torch.int32, device=dev)
+    fused_ok = k == 3 and tile == 256 and len(tile_tap) > 0
+    ypos_rank = torch.empty((n, 32), dtype=torch.int32, device=dev) if fused_ok else None
+    first_rank = torch.empty(len(tile_tap), dtype=torch.int32, device=dev) if fused_ok else None
     ws = L.workspace(L.load().ss_kmap_workspace_bytes(n, k), dev)
     order_c = order_row.contiguous()
     L.call("ss_kmap_pairs", L.ptr(nbr), L.ptr(order_c), n, k, L.ptr(base_dev), p_pad, L.ptr(pair_in),
-           L.ptr(ypos), L.ptr(ws), ws.numel(), L.stream())
-    return dict(pair_in=pair_in, ypos=ypos, tile_tap=upload(tile_tap or [0], torch.int32, dev),
+           L.ptr(ypos), L.ptr(ypos_rank), L.ptr(first_rank), L.ptr(ws), ws.numel(), L.stream())
+    tile_order = tile_pos = None
+    if fused_ok:  # (device-side, no host sync; 7.6 k tiles at the benchmark chunk)
+        tile_order = torch.sort(first_rank, stable=True).indices.to(torch.int32)
+        tile_pos = torch.empty_like(tile_order)
+        tile_pos[tile_order.long()] = torch.arange(len(tile_tap), dtype=torch.int32, device=dev)
+    return dict(pair_in=pair_in, ypos=ypos, ypos_rank=ypos_rank, tile_tap=upload(tile_tap or [0], torch.int32, dev),
+                tile_order=tile_order, tile_pos=tile_pos,
+                tile_flags=torch.empty(len(tile_tap) + 2, dtype=torch.int32, device=dev), order_row=order_c,
                 p_pad=p_pad, pairs=int(sum(int(c) for c in tap_count_host)), tile=tile, tap_base=list(base),
                 tap_count=[int(c) for c in tap_count_host])
 
@@ -280,17 +293,37 @@ def subm_conv_gemm(x_bf16, pairs, w_bf16, bias, n: int, out_dtype=torch.bfloat16
     return out
 
 
-def subm_conv_gemm_add_ln(x_bf16, pairs, w_bf16, bias, res_f32, ln0, ln1, eps=1e-5, inplace=True):
+def subm_conv_gemm_add_ln(x_bf16, pairs, w_bf16, bias, res_f32, ln0, ln1, eps=1e-5, inplace=True, impl="auto"):
     """The conv with the Block's next two steps fused into its gather-sum stage: y = res + LN0(conv(x)) (fp32, `res`
-    itself when inplace) and LN1(y) (bf16).  The conv output never reaches memory.  -> (y, LN1(y))."""
+    itself when inplace) and LN1(y) (bf16).  The conv output never reaches memory.  -> (y, LN1(y)).
+    impl: "auto" = ONE launch for cout >= 512 (the gather-sum runs on reducer warps inside the gather-GEMM and reads the
+    products back from L2: csrc/conv_gemm3.cu; measured 2.90 -> 2.62 ms at C = 768, 1.57 -> 1.48 at C = 512, but 0.67 ->
+    0.83 at C = 256, where the GEMM is too short to hide the reducers), two launches below that; "fused" / "split" force
+    one of the two (bit-identical; tests compare)."""
     k3, cout, cin = w_bf16.shape
     n = res_f32.shape[0]
     if res_f32.dtype != torch.float32 or not res_f32.is_contiguous() or tuple(res_f32.shape) != (n, cout):
         raise L.CudaKernelError("subm_conv_gemm_add_ln: the residual must be a contiguous fp32 [n, cout] tensor")
+    (g0, b0), (g1, b1) = ln0, ln1
+    fused = impl == "fused" or (impl == "auto" and cout >= FUSED_CONV_MIN_C)
+    if fused and cout >= 256 and k3 <= 32 and n > 0 and pairs.get("ypos_rank") is not None:
+        if pairs.get("tile") != CONV_TILE:
+            raise L.CudaKernelError("pair lists must be padded to %d-row tiles (ops.kmap_pairs)" % CONV_TILE)
+        p_pad = pairs["p_pad"]
+        prod = torch.empty((max(p_pad, 1), cout), dtype=_BF16, device=x_bf16.device)
+        out = res_f32 if inplace else torch.empty_like(res_f32)
+        norm = torch.empty((n, cout), dtype=_BF16, device=x_bf16.device)
+        x_bf16 = x_bf16.contiguous()
+        L.call("ss_subm_conv_fused_add_ln", L.ptr(x_bf16), L.ptr(pairs["pair_in"]), L.ptr(w_bf16), L.ptr(pairs["tile_tap"]),
+               L.ptr(pairs["tile_order"]), L.ptr(pairs["tile_pos"]), p_pad, k3, cin, cout, L.ptr(prod),
+               L.ptr(pairs["tile_flags"]), L.ptr(pairs["order_row"]), L.ptr(pairs["ypos_rank"]), L.ptr(bias), L.ptr(res_f32), L.ptr(g0), L.ptr(b0), L.ptr(g1),
+               L.ptr(b1), float(eps), n, L.ptr(out), L.ptr(norm), L.stream(),
+               meta=dict(flops=2.0 * pairs["pairs"] * cin * cout,
+                         bytes=2.0 * pairs["pairs"] * cin + n * (4.0 * k3 + 10.0 * cout)))
+        return out, norm
     prod = _subm_conv_products(x_bf16, pairs, w_bf16)
     out = res_f32 if inplace else torch.empty_like(res_f32)
     norm = torch.empty((n, cout), dtype=_BF16, device=x_bf16.device)
-    (g0, b0), (g1, b1) = ln0, ln1
     L.call("ss_subm_conv_reduce_add_ln", L.ptr(prod), L.ptr(pairs["ypos"]), L.ptr(bias), L.ptr(res_f32), L.ptr(g0), L.ptr(b0),
            L.ptr(g1), L.ptr(b1), float(eps), n, k3, cout, L.ptr(out), L.ptr(norm), L.stream(),
            meta=dict(bytes=2.0 * pairs["pairs"] * cout + n * (4.0 * k3 + 10.0 * cout)))

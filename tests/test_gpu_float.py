@@ -211,6 +211,30 @@ def test_subm_conv_fused_add_layernorm(c):
     assert y2.data_ptr() == r2.data_ptr() and torch.equal(y2, got_y) and torch.equal(h2, got_h)
 
 
+@pytest.mark.parametrize("c,n_raw,row", [(256, 5000, 0), (256, 70000, 2), (512, 40000, 1), (768, 70000, 3)])
+def test_subm_conv_single_launch_equals_split(c, n_raw, row):
+    """ss_subm_conv_fused_add_ln (gather-GEMM with reducer warps trailing it through per-tile counters, tiles taken in the
+    order of their first output's rank) against ss_subm_conv_gemm_pair + ss_subm_conv_reduce_add_ln: the same products and
+    the same summation order, so BIT-identical, on scenes with 1 .. 40 tiles per tap and along every serialized order."""
+    from scenesplat_b200 import ops
+    g, batch, offset, code, order, inv, depth = _scene(n_raw, seed=7 + row)
+    torch.manual_seed(3)
+    n = g.shape[0]
+    x = torch.randn(n, c).bfloat16().cuda()
+    w = (torch.randn(27, c, c) * (1.0 / (c * 7) ** 0.5)).bfloat16().cuda()
+    b = torch.randn(c).cuda()
+    res = (torch.randn(n, c) * 2).cuda()
+    ln0 = (torch.rand(c).cuda() + 0.5, torch.randn(c).cuda())
+    ln1 = (torch.rand(c).cuda() + 0.5, torch.randn(c).cuda())
+    nbr, cnt = ops.kmap_build(dev(g), dev(batch), dev(code[row]), dev(order[row]), depth, row, 3)
+    pairs = ops.kmap_pairs(nbr, dev(order[row]), 3, cnt.cpu().numpy())
+    assert sorted(pairs["tile_order"].cpu().tolist()) == list(range(pairs["p_pad"] // 256))
+    want_y, want_h = ops.subm_conv_gemm_add_ln(x, pairs, w, b, res, ln0, ln1, 1e-5, inplace=False, impl="split")
+    for _ in range(3):  # the per-tile counters are reset by every call
+        got_y, got_h = ops.subm_conv_gemm_add_ln(x, pairs, w, b, res, ln0, ln1, 1e-5, inplace=False, impl="fused")
+        assert torch.equal(got_y, want_y) and torch.equal(got_h, want_h)
+
+
 @pytest.mark.parametrize("logits", ["moderate", "huge", "hot_keys", "hot_rows"])
 @pytest.mark.parametrize("H,d,K", [(2, 16, 1024), (3, 32, 1024), (2, 48, 1024), (4, 16, 256), (1, 48, 100)])
 def test_patch_attention_tensor_core(H, d, K, logits):

@@ -49,6 +49,35 @@ for tile, fn in ((256, "ss_subm_conv_gemm256"), (256, "ss_subm_conv_gemm_pair"))
     else:
         print(f"   {fn} bit-identical to the single-CTA kernel:", bool(torch.equal(ref, prod)))
 
+# ---- the whole xCPE stage of a Block: gather-GEMM + gather-sum + LN + residual + LN, two launches vs one
+if c >= 256:
+    pairs = ops.kmap_pairs(nbr, dev(order[0]), 3, cnt.cpu().numpy(), tile=256)
+    resid = torch.randn(n, c, device="cuda")
+    ln0 = (torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda"))
+    ln1 = (torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda"))
+    outs = {}
+    for impl in ("split", "fused"):
+        if os.environ.get("CONV_ONLY") and os.environ["CONV_ONLY"] != impl:
+            continue
+        for _ in range(2):
+            y, h = ops.subm_conv_gemm_add_ln(x, pairs, w, b, resid, ln0, ln1, 1e-5, inplace=False, impl=impl)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            y, h = ops.subm_conv_gemm_add_ln(x, pairs, w, b, resid, ln0, ln1, 1e-5, inplace=False, impl=impl)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        outs[impl] = (y, h)
+        print(f"n={n} C={c} conv + gather-sum + LN + residual + LN, {'two launches' if impl == 'split' else 'ONE launch (fused)'}: "
+              f"{ms:.3f} ms  {2.0 * pairs['pairs'] * c * c / ms / 1e9:.0f} TFLOP/s useful")
+    if len(outs) == 2:
+        print("   fused bit-identical to split:", bool(torch.equal(outs["fused"][0], outs["split"][0]) and
+                                                      torch.equal(outs["fused"][1], outs["split"][1])))
+if os.environ.get("CONV_ONLY"):
+    sys.exit(0)
+
 # ---- backward kernels at the same shape: dgrad = the forward kernels on mirrored taps, wgrad = csrc/conv_wgrad.cu
 from scenesplat_b200 import training
 pairs = ops.kmap_pairs(nbr, dev(order[0]), 3, cnt.cpu().numpy(), tile=256)
