@@ -403,7 +403,9 @@ def main():
                      note="host_loop_ms = host time per loop iteration (enqueue + the pipeline's wait for chunk i - 2)")
         return max(rank_ms) * steps, prof, launches, clocks, stats
 
-    hot = frozenset({"ss_patch_attention", "ss_subm_conv_gemm256", "ss_subm_conv_gemm_pair"})  # the two candidates for "dominant own kernel"
+    hot = frozenset({"ss_patch_attention", "ss_subm_conv_gemm256", "ss_subm_conv_gemm_pair",
+                     "ss_subm_conv_fused_add_ln"})  # the candidates for "dominant own kernel" (the fused conv's time includes
+    # its gather-sum + LN stage, its FLOPs only the GEMM)
     ms, prof_hot, launches, clocks, step_stats = timed(step_resident, args.steps, profile=hot)
     ms_e2e, _, _, _, e2e_stats = timed(step_e2e, args.steps)
     # full per-kernel table from a separate instrumented pass (events around ~350 calls/step perturb the step)

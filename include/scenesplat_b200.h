@@ -122,10 +122,11 @@ int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* bat
  * of (tap, output voxel) or -1; ypos_rank (nullable, k = 3) [n, 32] = the same positions indexed by the output's RANK
  * along order_row (columns >= 27 are -1): what the fused conv's reducer warps read, one 128-byte line per output;
  * tile_first_rank (nullable; tap bases multiples of 256) [p_pad / 256] = rank of the first output of every 256-row tile
- * of the product buffer (the fused conv produces the tiles in that order). */
+ * of the product buffer; tile_order / tile_pos (nullable, both or none, need tile_first_rank) [p_pad / 256] = the tiles
+ * sorted by (first rank, index) and the inverse permutation: the order in which the fused conv produces them. */
 int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k, const int64_t* tap_base_dev,
                   int64_t p_pad, int32_t* pair_in, int32_t* ypos, int32_t* ypos_rank, int32_t* tile_first_rank,
-                  void* workspace, size_t workspace_bytes, void* stream);
+                  int32_t* tile_order, int32_t* tile_pos, void* workspace, size_t workspace_bytes, void* stream);
 
 /* SIMT fp32-accumulate conv: out[p,co] = bias[co] + sum_t sum_ci wt[t][ci][co] * in[nbr[t][p]][ci],
  * then optional affine (folded BN) + activation.  wt is the [k^3, cin, cout] fp32 re-layout of the

@@ -156,8 +156,14 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
       const int nqb = (n_q + kQB - 1) / kQB;
       const int ntiles = g == 0 ? (nqb + 1) / 2 : nqb / 2;
       // ping-pong (named barriers 9 / 10, 256 waiting + 256 arriving threads): the groups take turns in the
-      // exponential sweep, so one group's MUFU burst overlaps the other group's TMEM / handshake part
-      const int total_other = (g == 0 ? nqb / 2 : (nqb + 1) / 2) * nch;
+      // exponential sweep, so one group's MUFU burst overlaps the other group's TMEM / handshake part.  Group 0 waits
+      // (barrier 9) before its steps 0 .. T1 - 1 (T1 = group 1's steps in this item): step 0 for group 1's entry into
+      // the item, step k for the end of group 1's step k - 1; group 1 waits (barrier 10) for the end of group 0's step k.
+      // Every arrival is consumed before its sender can arrive on the same barrier again, ALSO across items: with an
+      // odd number of query tiles group 1 leaves the item first, and an arrival after its last step (nobody needs it)
+      // followed by its entry arrival for the next item would complete barrier 9 without group 0 (a deadlock that only
+      // a persistent CTA can reach; found with 13 batch elements x 5 tiles at d = 32).
+      const int total_g1 = (nqb / 2) * nch;
       const bool pp = pingpong && nqb > 1;
       if (pp && g == 1) asm volatile("bar.arrive 9, 512;" ::: "memory");  // group 0 takes the first turn
       int si = 0;  // step within the item
@@ -221,7 +227,7 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
           // ---- sweep 2: exponentials, 32 columns at a time
           if (pp) {
             if (g == 0) {
-              if (si <= total_other) asm volatile("bar.sync 9, 512;" ::: "memory");
+              if (si < total_g1) asm volatile("bar.sync 9, 512;" ::: "memory");
             } else {
               asm volatile("bar.sync 10, 512;" ::: "memory");
             }
@@ -254,9 +260,9 @@ patch_attention_tc16_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t
           }
           if (pp) {
             if (g == 0) {
-              if (si < total_other) asm volatile("bar.arrive 10, 512;" ::: "memory");
+              if (si < total_g1) asm volatile("bar.arrive 10, 512;" ::: "memory");
             } else {
-              if (si + 1 < total_other) asm volatile("bar.arrive 9, 512;" ::: "memory");
+              if (si + 1 < total_g1) asm volatile("bar.arrive 9, 512;" ::: "memory");
             }
           }
           tc::tmem_st_wait();

@@ -104,6 +104,30 @@ struct PairRuns {
   __device__ void finish(int, uint32_t) const {}
 };
 
+// Order of the product tiles for the fused conv: position of tile t = number of tiles with a smaller (first rank, index)
+// key.  T is a few thousand (7.6 k at the benchmark chunk): T^2 comparisons from shared-memory chunks, no sort.
+__global__ void __launch_bounds__(256) tile_rank_kernel(const int32_t* __restrict__ first_rank, int tiles,
+                                                        int32_t* __restrict__ tile_order, int32_t* __restrict__ tile_pos) {
+  __shared__ int32_t s_fr[1024];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int32_t mine = t < tiles ? first_rank[t] : 0;
+  int pos = 0;
+  for (int base = 0; base < tiles; base += 1024) {
+    const int m = min(1024, tiles - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += 256) s_fr[i] = first_rank[base + i];
+    __syncthreads();
+    for (int i = 0; i < m; ++i) {
+      const int32_t v = s_fr[i];
+      pos += (v < mine || (v == mine && base + i < t)) ? 1 : 0;
+    }
+  }
+  if (t < tiles) {
+    tile_pos[t] = pos;
+    tile_order[pos] = t;
+  }
+}
+
 }  // namespace ss
 
 extern "C" {
@@ -148,12 +172,13 @@ int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* bat
 
 int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k, const int64_t* tap_base_dev,
                   int64_t p_pad, int32_t* pair_in, int32_t* ypos, int32_t* ypos_rank, int32_t* tile_first_rank,
-                  void* workspace, size_t workspace_bytes, void* stream_) {
+                  int32_t* tile_order, int32_t* tile_pos, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n < 0 || (k != 3 && k != 5) || p_pad < 0) return SS_BAD_ARGS;
   if (n == 0) return SS_OK;
   if (!nbr || !order_row || !tap_base_dev || !pair_in || !ypos || !workspace) return SS_BAD_ARGS;
   if ((ypos_rank && k != 3) || (tile_first_rank && p_pad % 256 != 0)) return SS_BAD_ARGS;
+  if ((tile_order || tile_pos) && !(tile_first_rank && tile_order && tile_pos)) return SS_BAD_ARGS;
   // columns 27..31 of the rank-major table stay -1
   if (ypos_rank) SS_CUDA(cudaMemsetAsync(ypos_rank, 0xff, (size_t)n * 32 * 4, stream));
   // padding rows of every tap segment gather row 0 (their products are never read back)
@@ -162,7 +187,12 @@ int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   ws += ss::align_up((size_t)n * 8, 256);
   ss::PairRuns f{nbr, order_row, tap_base_dev, n, pair_in, ypos, ypos_rank, tile_first_rank};
-  return ss::runs_launch(f, n, ws, nullptr, stream, k * k * k);
+  int rc = ss::runs_launch(f, n, ws, nullptr, stream, k * k * k);
+  if (rc != SS_OK || !tile_order || p_pad == 0) return rc;
+  const int tiles = (int)(p_pad / 256);
+  ss::tile_rank_kernel<<<ss::ceil_div(tiles, 256), 256, 0, stream>>>(tile_first_rank, tiles, tile_order, tile_pos);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
 }
 
 }  // extern "C"

@@ -237,16 +237,13 @@ def kmap_pairs(nbr, order_row, k: int, tap_count_host, tile: int = None):
     ypos = torch.empty((k3, n), dtype=torch.int32, device=dev)
     fused_ok = k == 3 and tile == 256 and len(tile_tap) > 0
     ypos_rank = torch.empty((n, 32), dtype=torch.int32, device=dev) if fused_ok else None
-    first_rank = torch.empty(len(tile_tap), dtype=torch.int32, device=dev) if fused_ok else None
+    first_rank, tile_order, tile_pos = (torch.empty(len(tile_tap), dtype=torch.int32, device=dev) if fused_ok else None
+                                        for _ in range(3))
     ws = L.workspace(L.load().ss_kmap_workspace_bytes(n, k), dev)
     order_c = order_row.contiguous()
     L.call("ss_kmap_pairs", L.ptr(nbr), L.ptr(order_c), n, k, L.ptr(base_dev), p_pad, L.ptr(pair_in),
-           L.ptr(ypos), L.ptr(ypos_rank), L.ptr(first_rank), L.ptr(ws), ws.numel(), L.stream())
-    tile_order = tile_pos = None
-    if fused_ok:  # (device-side, no host sync; 7.6 k tiles at the benchmark chunk)
-        tile_order = torch.sort(first_rank, stable=True).indices.to(torch.int32)
-        tile_pos = torch.empty_like(tile_order)
-        tile_pos[tile_order.long()] = torch.arange(len(tile_tap), dtype=torch.int32, device=dev)
+           L.ptr(ypos), L.ptr(ypos_rank), L.ptr(first_rank), L.ptr(tile_order), L.ptr(tile_pos), L.ptr(ws), ws.numel(),
+           L.stream())
     return dict(pair_in=pair_in, ypos=ypos, ypos_rank=ypos_rank, tile_tap=upload(tile_tap or [0], torch.int32, dev),
                 tile_order=tile_order, tile_pos=tile_pos,
                 tile_flags=torch.empty(len(tile_tap) + 2, dtype=torch.int32, device=dev), order_row=order_c,

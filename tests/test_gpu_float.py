@@ -281,6 +281,39 @@ def test_patch_attention_tensor_core(H, d, K, logits):
     assert rel < 1e-2, rel
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("n,nb,H,d", [(60000, 13, 16, 32), (60000, 13, 16, 48), (30000, 7, 16, 16), (20000, 31, 8, 48),
+                                      (45000, 9, 12, 32), (3000, 3, 2, 16)])
+def test_patch_attention_item_sequences(n, nb, H, d):
+    """The persistent tcgen05 kernel walks many (head, patch) items per CTA; batches of `nb` elements put ragged patches
+    (odd and even numbers of query tiles, short key windows, the last-patch window rule) BETWEEN full ones in every CTA's
+    item sequence.  13 elements x (4 full patches + 5 query tiles) at d = 32 deadlocked the first persistent version (the
+    groups' ping-pong barrier, see csrc/attention_tc.cu); the mbarrier waits trap after 20 s, so a protocol bug fails
+    this test instead of hanging it.  Checked against the independent SIMT kernel on the same bf16 inputs (same tolerance
+    as test_patch_attention_tensor_core) and, for the small case, against the fp32 oracle."""
+    from scenesplat_b200 import ops
+    K = 1024
+    rng = np.random.default_rng(n + nb)
+    offset = np.array([(n * (b + 1)) // nb for b in range(nb)], dtype=np.int64)
+    C = H * d
+    torch.manual_seed(1)
+    qkv = (torch.randn(n, 3 * C) * 1.5).bfloat16()
+    order = np.concatenate([rng.permutation(np.arange(a, b)) for a, b in zip([0, *offset[:-1]], offset)])
+    scale = d ** -0.5
+    table = ops.patch_table(dev(offset), K, n)
+    got = ops.patch_attention(qkv.cuda(), dev(order), table, K, H, scale, impl="tc")
+    simt = ops.patch_attention(qkv.cuda(), dev(order), table, K, H, scale, impl="simt")
+    torch.cuda.synchronize()
+    tol = 8e-3 + 2.0 ** -7 * simt.float().abs()
+    excess = ((got.float() - simt.float()).abs() - tol).max().item()
+    assert excess <= 0, excess
+    if n <= 5000:
+        inverse = np.empty(n, dtype=np.int64)
+        inverse[order] = np.arange(n)
+        want = oattn.serialized_attention_core(qkv.float(), order, inverse, offset, K, H, scale)
+        assert ((got.float().cpu() - want).norm() / want.norm()).item() < 1e-2
+
+
 @pytest.mark.parametrize("n,cin,cout", [(1, 16, 32), (300, 128, 32), (257, 256, 64), (5001, 3072, 768), (40001, 2048, 512)])
 @pytest.mark.parametrize("inplace", [True, False])
 def test_linear_residual_cta_pair(n, cin, cout, inplace):

@@ -31,13 +31,20 @@ int main(int argc, char** argv) {
   std::vector<int64_t> order(n);
   std::iota(order.begin(), order.end(), 0);
   if (!ident) std::shuffle(order.begin(), order.end(), rng);
-  const int np = (n + K - 1) / K;
-  std::vector<int> table(4 * np);
-  for (int p = 0; p < np; ++p) {
-    int qb = p * K, qe = std::min(n, qb + K), kb = qb, ke = qe;
-    if (p == np - 1 && n > K) kb = n - K;  // window rule of the last patch
-    table[4 * p] = qb; table[4 * p + 1] = qe; table[4 * p + 2] = kb; table[4 * p + 3] = ke;
+  // argv[7]: number of batch elements the n tokens are split into (each with its own patches and last-patch window rule)
+  const int nbatch = argc > 7 ? atoi(argv[7]) : 1;
+  std::vector<int> table;
+  for (int b = 0; b < nbatch; ++b) {
+    const int b0 = (int)((long long)n * b / nbatch), b1 = (int)((long long)n * (b + 1) / nbatch), nb = b1 - b0;
+    const int npb = (nb + K - 1) / K;
+    for (int p = 0; p < npb; ++p) {
+      int qb = b0 + p * K, qe = std::min(b1, qb + K), kb = qb, ke = qe;
+      if (p == npb - 1 && nb > K) kb = b1 - K;  // window rule of the last patch
+      table.push_back(qb); table.push_back(qe); table.push_back(kb); table.push_back(ke);
+    }
   }
+  for (int z = 0; z < 2; ++z) for (int u = 0; u < 4; ++u) table.push_back(0);  // unused entries (n_q = 0), as the device table has
+  const int np = (int)table.size() / 4;
   __nv_bfloat16 *dq, *dout; int64_t* dord; int* dtab;
   cudaMalloc(&dq, hq.size() * 2); cudaMalloc(&dout, (size_t)n * C * 2); cudaMalloc(&dord, n * 8); cudaMalloc(&dtab, table.size() * 4);
   cudaMemcpy(dq, hq.data(), hq.size() * 2, cudaMemcpyHostToDevice);
