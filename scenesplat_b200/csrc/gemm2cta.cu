@@ -27,7 +27,6 @@
 
 namespace ss {
 
-constexpr int kPThreads = 320;
 constexpr int kPBK = 64;     // bf16 elements per K chunk = one 128-byte swizzle row
 constexpr int kPStages = 5;
 constexpr int kPTileM = 256; // rows per pair tile (128 per CTA)
@@ -44,9 +43,11 @@ struct PairSmem {
 
 
 // ACT: 0 = none, 1 = exact GELU.  RES: 1 = out_f32 = res + (x W^T + b) (res may be out_f32 itself), bf16 copy in `out`
-// (optional).
-template <int ACT, int RES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
+// (optional).  EW: epilogue warps, 8 (row quarter x column half) or 16 (row quarter x column quarter; RES = 0 only: the
+// GELU epilogue is 2 MUFU + 13 other instructions per element, ~5 k issue cycles per 128 x 256 tile against 6.1 k cycles
+// of MMA, and with two warps per SM sub-partition its dependent chains are not hidden under the next tile's MMAs).
+template <int ACT, int RES, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EW + 2) * 32, 1)
 linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const float* __restrict__ bias, int64_t n_rows, int cin, int cout, __nv_bfloat16* __restrict__ out,
                    const float* res, float* out_f32) {
@@ -74,22 +75,22 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&acc_full[b], 1);
-      tc::mbar_init(&acc_empty[b], 16);
+      tc::mbar_init(&acc_empty[b], 2 * EW);
     }
     tc::mbar_fence_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == EW && lane == 0) {
     tc::tma_prefetch_desc(&tmap_x);
     tc::tma_prefetch_desc(&tmap_w);
   }
-  if (warp == 9) pair::tmem_alloc<512>(tmem_slot);
+  if (warp == EW + 1) pair::tmem_alloc<512>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
   pair::cluster_sync();  // both CTAs' barriers are initialised before anyone signals across the pair
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == EW) {
     // ------------------------------------------------------------------ TMA producer (one lane, both CTAs)
     if (lane == 0) {
       int64_t g = 0;
@@ -106,7 +107,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == EW + 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kPTileM, kPTileN);
@@ -137,9 +138,12 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     // ------------------------------------------------------------------ epilogue warps 0..7: (row quarter, column half)
     // bf16 tile [32 rows][64 B], 16-byte chunks XOR-swizzled by (row >> 1) & 3; RES: fp32 tile [32 rows][128 B] behind it,
     // 16-byte chunks XOR-swizzled by row & 7
-    uint8_t* stg = smem + S::kOffEpi + warp * 6144;
+    static_assert(EW == 8 || (EW == 16 && RES == 0), "16 epilogue warps: no fp32 staging tiles");
+    constexpr int kCols = 256 / (EW / 4);  // columns per epilogue warp
+    constexpr int kGroups = kCols / 32;
+    uint8_t* stg = smem + S::kOffEpi + warp * (EW == 8 ? 6144 : 2048);
     uint8_t* stf = stg + 2048;
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, half = warp >> 2;  // (half = column part: 0..1 or 0..3)
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int it = 0;
     for (int64_t item = pair_id; item < n_items; item += n_pairs, ++it) {
@@ -151,16 +155,16 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       const int64_t row0 = tile * kPTileM + rank * 128 + quarter * 32;
       // 32-column groups of this warp inside the matrix; the TMEM load of group j + 1 is in flight while group j is
       // converted and stored (two register buffers, loop fully unrolled)
-      const int nj = max(0, min(4, (cout - (n0 + half * 128) + 31) / 32));
+      const int nj = max(0, min(kGroups, (cout - (n0 + half * kCols) + 31) / 32));
       uint32_t vbuf[2][32];
-      if (RES == 0 && nj > 0) tc::tmem_ld32(t_lane + b * kPTileN + half * 128, vbuf[0]);
+      if (RES == 0 && nj > 0) tc::tmem_ld32(t_lane + b * kPTileN + half * kCols, vbuf[0]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kGroups; ++j) {
         if (j >= nj) break;
-        const int c0 = n0 + half * 128 + j * 32;
+        const int c0 = n0 + half * kCols + j * 32;
         uint32_t (&v)[32] = vbuf[RES == 1 ? 0 : (j & 1)];
         if constexpr (RES == 1) {
-          tc::tmem_ld32(t_lane + b * kPTileN + half * 128 + j * 32, v);
+          tc::tmem_ld32(t_lane + b * kPTileN + half * kCols + j * 32, v);
           // residual tile -> shared memory with coalesced 128-byte row segments (8 lanes per row, 4 rows per access)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -204,7 +208,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           }
         } else {
         tc::tmem_ld_wait();
-        if (j + 1 < nj) tc::tmem_ld32(t_lane + b * kPTileN + half * 128 + (j + 1) * 32, vbuf[(j + 1) & 1]);
+        if (j + 1 < nj) tc::tmem_ld32(t_lane + b * kPTileN + half * kCols + (j + 1) * 32, vbuf[(j + 1) & 1]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];
@@ -248,20 +252,26 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   tc::tc_fence_before();
   __syncthreads();
   pair::cluster_sync();  // no CTA of the pair frees TMEM or exits while the other still computes or signals
-  if (warp == 9) {
+  if (warp == EW + 1) {
     tc::tc_fence_after();
     pair::tmem_dealloc<512>(tmem_base);
   }
 }
 
-template <int ACT, int RES>
+#ifndef SS_GEMM_EW_PLAIN
+#define SS_GEMM_EW_PLAIN 8
+#endif
+#ifndef SS_GEMM_EW_ACT
+#define SS_GEMM_EW_ACT 16  // epilogue warps of the fc1 + GELU variant (tools/run_linear.py A/B: -DSS_GEMM_EW_ACT=8)
+#endif
+template <int ACT, int RES, int EW = 8>
 static int launch_linear_pair(const CUtensorMap& tx, const CUtensorMap& tw, const float* bias, int64_t n, int cin, int cout,
                               void* out, const float* res, float* out_f32, cudaStream_t stream) {
-  auto kern = linear_pair_kernel<ACT, RES>;
+  auto kern = linear_pair_kernel<ACT, RES, EW>;
   SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::kTotal));
   const int64_t n_items = ((n + kPTileM - 1) / kPTileM) * ((cout + kPTileN - 1) / kPTileN);
   const int pairs = (int)imin64(n_items, kNumSMs / 2);
-  kern<<<2 * pairs, kPThreads, PairSmem::kTotal, stream>>>(tx, tw, bias, n, cin, cout, (__nv_bfloat16*)out, res, out_f32);
+  kern<<<2 * pairs, (EW + 2) * 32, PairSmem::kTotal, stream>>>(tx, tw, bias, n, cin, cout, (__nv_bfloat16*)out, res, out_f32);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
@@ -282,8 +292,8 @@ static int linear_pair_entry(const void* x_bf16, const void* w_bf16, const float
   rc = ss::make_tmap_bf16_2d(&tw, w_bf16, (uint64_t)cout, (uint64_t)cin, 128, ss::kPBK);
   if (rc) return rc;
   if (res) return ss::launch_linear_pair<0, 1>(tx, tw, bias, n, cin, cout, out_bf16, res, out_f32, stream);
-  return act == 1 ? ss::launch_linear_pair<1, 0>(tx, tw, bias, n, cin, cout, out_bf16, nullptr, nullptr, stream)
-                  : ss::launch_linear_pair<0, 0>(tx, tw, bias, n, cin, cout, out_bf16, nullptr, nullptr, stream);
+  return act == 1 ? ss::launch_linear_pair<1, 0, SS_GEMM_EW_ACT>(tx, tw, bias, n, cin, cout, out_bf16, nullptr, nullptr, stream)
+                  : ss::launch_linear_pair<0, 0, SS_GEMM_EW_PLAIN>(tx, tw, bias, n, cin, cout, out_bf16, nullptr, nullptr, stream);
 }
 
 extern "C" int ss_linear_act_bf16(const void* x_bf16, const void* w_bf16, const float* bias, int64_t n, int cin, int cout,

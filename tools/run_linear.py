@@ -4,7 +4,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
-from scenesplat_b200 import ops
+from scenesplat_b200 import ops, _lib
+if os.environ.get("SS_LIB"):  # A/B against a variant build of the library (developer tool only)
+    _lib.LIB_PATH = os.path.abspath(os.environ["SS_LIB"])
 
 shapes = [(1000, 64, 256), (513, 768, 3072), (299277, 768, 3072), (299277, 3072, 768), (119000, 512, 2048), (299277, 768, 2304)]
 if len(sys.argv) > 3:
