@@ -156,13 +156,14 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       // 32-column groups of this warp inside the matrix; the TMEM load of group j + 1 is in flight while group j is
       // converted and stored (two register buffers, loop fully unrolled)
       const int nj = max(0, min(kGroups, (cout - (n0 + half * kCols) + 31) / 32));
-      uint32_t vbuf[2][32];
-      if (RES == 0 && nj > 0) tc::tmem_ld32(t_lane + b * kPTileN + half * kCols, vbuf[0]);
+      constexpr bool kDB = RES == 0 && (EW == 8 || ACT == 1);  // TMEM load of group j + 1 under the conversion of group j
+      uint32_t vbuf[kDB ? 2 : 1][32];
+      if (kDB && nj > 0) tc::tmem_ld32(t_lane + b * kPTileN + half * kCols, vbuf[0]);
 #pragma unroll
       for (int j = 0; j < kGroups; ++j) {
         if (j >= nj) break;
         const int c0 = n0 + half * kCols + j * 32;
-        uint32_t (&v)[32] = vbuf[RES == 1 ? 0 : (j & 1)];
+        uint32_t (&v)[32] = vbuf[kDB ? (j & 1) : 0];
         if constexpr (RES == 1) {
           tc::tmem_ld32(t_lane + b * kPTileN + half * kCols + j * 32, v);
           // residual tile -> shared memory with coalesced 128-byte row segments (8 lanes per row, 4 rows per access)
@@ -207,8 +208,9 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             if (row0 + r < n_rows) *reinterpret_cast<float4*>(out_f32 + (size_t)(row0 + r) * cout + c0 + cc * 4) = y;
           }
         } else {
+        if (!kDB) tc::tmem_ld32(t_lane + b * kPTileN + half * kCols + j * 32, v);
         tc::tmem_ld_wait();
-        if (j + 1 < nj) tc::tmem_ld32(t_lane + b * kPTileN + half * kCols + (j + 1) * 32, vbuf[(j + 1) & 1]);
+        if (kDB && j + 1 < nj) tc::tmem_ld32(t_lane + b * kPTileN + half * kCols + (j + 1) * 32, vbuf[kDB ? ((j + 1) & 1) : 0]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];
@@ -278,6 +280,11 @@ static int launch_linear_pair(const CUtensorMap& tx, const CUtensorMap& tw, cons
 
 }  // namespace ss
 
+namespace ss {
+int launch_linear_narrow(const void* x, const void* w, const float* bias, int64_t n, int cin, int cout, int act, void* out,
+                         cudaStream_t stream);  // gemm_narrow.cu
+}
+
 static int linear_pair_entry(const void* x_bf16, const void* w_bf16, const float* bias, int64_t n, int cin, int cout, int act,
                              void* out_bf16, const float* res, float* out_f32, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -286,6 +293,9 @@ static int linear_pair_entry(const void* x_bf16, const void* w_bf16, const float
   if (!x_bf16 || !w_bf16) return SS_BAD_ARGS;
   if (((uintptr_t)x_bf16 | (uintptr_t)w_bf16 | (uintptr_t)out_bf16 | (uintptr_t)bias | (uintptr_t)res | (uintptr_t)out_f32) % 16 != 0)
     return SS_BAD_ARGS;
+  // the C = 32 stage (enc0 qkv / proj / fc1, the 32 -> 64 pooling projection) is a row streamer: W in shared memory, warp-level
+  // MMA (gemm_narrow.cu; measured faster than the pair kernel only up to cin = 32: profiles/r2_gemm.md)
+  if (!res && cin <= 32 && cout <= 256) return ss::launch_linear_narrow(x_bf16, w_bf16, bias, n, cin, cout, act, out_bf16, stream);
   CUtensorMap tx, tw;
   int rc = ss::make_tmap_bf16_2d(&tx, x_bf16, (uint64_t)n, (uint64_t)cin, 128, ss::kPBK);
   if (rc) return rc;
