@@ -260,6 +260,9 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   }
 }
 
+#ifndef SS_NARROW_MAX_CIN
+#define SS_NARROW_MAX_CIN 32  // (64 / 128: measured slower than the pair kernel, profiles/r2_gemm.md)
+#endif
 #ifndef SS_GEMM_EW_PLAIN
 #define SS_GEMM_EW_PLAIN 8
 #endif
@@ -295,7 +298,7 @@ static int linear_pair_entry(const void* x_bf16, const void* w_bf16, const float
     return SS_BAD_ARGS;
   // the C = 32 stage (enc0 qkv / proj / fc1, the 32 -> 64 pooling projection) is a row streamer: W in shared memory, warp-level
   // MMA (gemm_narrow.cu; measured faster than the pair kernel only up to cin = 32: profiles/r2_gemm.md)
-  if (!res && cin <= 32 && cout <= 256) return ss::launch_linear_narrow(x_bf16, w_bf16, bias, n, cin, cout, act, out_bf16, stream);
+  if (!res && cin % 32 == 0 && cin <= SS_NARROW_MAX_CIN && cout <= 256) return ss::launch_linear_narrow(x_bf16, w_bf16, bias, n, cin, cout, act, out_bf16, stream);
   CUtensorMap tx, tw;
   int rc = ss::make_tmap_bf16_2d(&tx, x_bf16, (uint64_t)n, (uint64_t)cin, 128, ss::kPBK);
   if (rc) return rc;

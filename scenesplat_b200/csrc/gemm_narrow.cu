@@ -1,4 +1,4 @@
-// Narrow Linear layers (cin <= 128, cout <= 256): out = act(x W^T + b), bf16 in / bf16 out, fp32 accumulate.
+// Narrow Linear layers (cin in {32, 64, 96, 128}, cout <= 256): out = act(x W^T + b), bf16 in / bf16 out, fp32 accumulate.
 //
 // Replaces (reference): the nn.Linear layers of the first two encoder stages (C = 32 / 64: qkv, proj, fc1 + GELU, fc2;
 // point_transformer_v3m1_base.py:181-248) and the narrow pooling / unpooling projections (:416,471-482).
@@ -10,8 +10,9 @@
 // global memory (each 64..256-byte row is read by 4 lanes x cin / 16 steps, the sectors stay in L1 in between), warp-level
 // mma.sync m16n8k16 against B fragments from shared memory, bias / GELU on the accumulator registers, the strip's output
 // staged per warp in shared memory and written with 16-byte row-contiguous stores.  No tensor-memory / TMA machinery: the
-// kernel is a row streamer, the tensor pipe is idle either way.  Used for cin <= 32 only (ss_linear_act_bf16): from cin = 64
-// on the 4-byte A-fragment loads (32 per strip and lane at cin = 128) bind it and the pair kernel is faster again.
+// kernel is a row streamer.  Used for cin = 32 only (ss_linear_act_bf16): its time grows by ~8 us per 32 output columns at
+// 299 k rows (the warp-level MMA path and the epilogue, not the bytes), so from cin = 64 / cout = 192 on the pair kernel is
+// faster again (profiles/r2_gemm.md).
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "../../include/scenesplat_b200.h"
@@ -33,13 +34,20 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// KS = cin / 16 (1..8).  Shared memory: W [cout][cin + 8] bf16, then one [16][kNarrowChunk + 8] bf16 staging tile per warp.
-template <int KS, int ACT>
+// KB = cin / 32 (1..4).  Shared memory: W [cout][ldw] bf16, then one [16][kNarrowChunk + 8] bf16 staging tile per warp.
+//
+// The MMA's k index is a summation index: any assignment of physical columns to it is valid as long as A and B use the
+// same one.  Per 32-column block a lane therefore takes the 16 CONTIGUOUS bytes [tig * 8, tig * 8 + 8) of its rows (one
+// LDG.128 per row: 4 lanes cover a 64-byte row segment) and of W's row (one LDS.128 per n-tile), and feeds element pairs
+// 0 / 1 to the first k-step's (a0 a1 | a2 a3, b0 | b1) and pairs 2 / 3 to the second: 4x fewer load instructions than
+// the canonical fragment layout (which takes 4-byte pieces 16 bytes apart), full sectors.
+template <int KB, int ACT>
 __global__ void __launch_bounds__(kNarrowThreads, 2)
 linear_narrow_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                      int64_t n, int cout, __nv_bfloat16* __restrict__ out) {
-  constexpr int cin = KS * 16;
-  constexpr int ldw = cin + 8;             // +16 bytes per row: the 8 rows of a B fragment fall into distinct banks
+  constexpr int cin = KB * 32;
+  // row stride = 64 (mod 128) bytes: the 8 lanes of an LDS.128 phase (2 rows x 4 pieces) hit 8 distinct 16-byte bank groups
+  constexpr int ldw = cin + ((cin * 2) % 128 == 64 ? 0 : 32);
   constexpr int lds = kNarrowChunk + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -53,29 +61,36 @@ linear_narrow_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   const int gid = lane >> 2, tig = lane & 3;
   const int64_t strips = (n + 15) >> 4;
   const int64_t nw = (int64_t)gridDim.x * (kNarrowThreads / 32);
-  for (int64_t s = (int64_t)blockIdx.x * (kNarrowThreads / 32) + warp; s < strips; s += nw) {
-    const int64_t r0 = s * 16 + gid, r1 = r0 + 8;
-    uint32_t a[KS][4];
+  auto load_strip = [&](int64_t st, uint4 (&q0)[KB], uint4 (&q1)[KB]) {
+    const int64_t r0 = st * 16 + gid, r1 = r0 + 8;
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) {
-      const int c = kk * 16 + tig * 2;
-      a[kk][0] = r0 < n ? *reinterpret_cast<const uint32_t*>(x + r0 * cin + c) : 0u;
-      a[kk][1] = r1 < n ? *reinterpret_cast<const uint32_t*>(x + r1 * cin + c) : 0u;
-      a[kk][2] = r0 < n ? *reinterpret_cast<const uint32_t*>(x + r0 * cin + c + 8) : 0u;
-      a[kk][3] = r1 < n ? *reinterpret_cast<const uint32_t*>(x + r1 * cin + c + 8) : 0u;
+    for (int kb = 0; kb < KB; ++kb) {
+      q0[kb] = r0 < n ? *reinterpret_cast<const uint4*>(x + r0 * cin + kb * 32 + tig * 8) : make_uint4(0u, 0u, 0u, 0u);
+      q1[kb] = r1 < n ? *reinterpret_cast<const uint4*>(x + r1 * cin + kb * 32 + tig * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
+  };
+  int64_t s = (int64_t)blockIdx.x * (kNarrowThreads / 32) + warp;
+  uint4 q0[KB], q1[KB], p0[KB], p1[KB];
+  if (s < strips) load_strip(s, q0, q1);
+  for (; s < strips; s += nw) {
+    // the next strip's rows are in flight while this one is multiplied, converted and stored (a row streamer lives on
+    // bytes in flight: 16 warps per SM x one strip each did not cover the DRAM latency)
+    if (s + nw < strips) load_strip(s + nw, p0, p1);
     for (int n0 = 0; n0 < cout; n0 += kNarrowChunk) {
       const int nt_n = min(kNarrowChunk, cout - n0) >> 3;  // n-tiles of 8 columns in this chunk
       float acc[kNarrowChunk / 8][4];
 #pragma unroll
       for (int t = 0; t < kNarrowChunk / 8; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
 #pragma unroll
-      for (int kk = 0; kk < KS; ++kk) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint32_t a_lo[4] = {q0[kb].x, q1[kb].x, q0[kb].y, q1[kb].y};
+        const uint32_t a_hi[4] = {q0[kb].z, q1[kb].z, q0[kb].w, q1[kb].w};
 #pragma unroll
         for (int t = 0; t < kNarrowChunk / 8; ++t) {
           if (t < nt_n) {
-            const __nv_bfloat16* bp = sW + (size_t)(n0 + t * 8 + gid) * ldw + kk * 16 + tig * 2;
-            mma_bf16_16816(acc[t], a[kk], *reinterpret_cast<const uint32_t*>(bp), *reinterpret_cast<const uint32_t*>(bp + 8));
+            const uint4 wv = *reinterpret_cast<const uint4*>(sW + (size_t)(n0 + t * 8 + gid) * ldw + kb * 32 + tig * 8);
+            mma_bf16_16816(acc[t], a_lo, wv.x, wv.y);
+            mma_bf16_16816(acc[t], a_hi, wv.z, wv.w);
           }
         }
       }
@@ -110,18 +125,25 @@ linear_narrow_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
       }
       __syncwarp();
     }
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+      q0[kb] = p0[kb];
+      q1[kb] = p1[kb];
+    }
   }
 }
 
-template <int KS>
-static int launch_narrow_ks(const void* x, const void* w, const float* bias, int64_t n, int cout, int act, void* out,
+template <int KB>
+static int launch_narrow_kb(const void* x, const void* w, const float* bias, int64_t n, int cout, int act, void* out,
                             cudaStream_t stream) {
-  const size_t smem = ((size_t)cout * (KS * 16 + 8) + (size_t)(kNarrowThreads / 32) * 16 * (kNarrowChunk + 8)) * 2;
+  constexpr int cin = KB * 32;
+  constexpr int ldw = cin + ((cin * 2) % 128 == 64 ? 0 : 32);
+  const size_t smem = ((size_t)cout * ldw + (size_t)(kNarrowThreads / 32) * 16 * (kNarrowChunk + 8)) * 2;
   const int64_t strips = (n + 15) >> 4;
   const int blocks = (int)imin64(ceil_div64(strips, kNarrowThreads / 32), 2 * kNumSMs);
 #define SS_NARROW_(A)                                                                                              \
   do {                                                                                                             \
-    auto kern = linear_narrow_kernel<KS, A>;                                                                       \
+    auto kern = linear_narrow_kernel<KB, A>;                                                                       \
     SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
     kern<<<blocks, kNarrowThreads, smem, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, n, cout, \
                                                    (__nv_bfloat16*)out);                                           \
@@ -133,18 +155,14 @@ static int launch_narrow_ks(const void* x, const void* w, const float* bias, int
   return SS_OK;
 }
 
-// Called by ss_linear_act_bf16 (gemm2cta.cu) for cin in {16, 32, .., 128}, cout % 8 == 0, cout <= 256.
+// Called by ss_linear_act_bf16 (gemm2cta.cu) for cin in {32, 64, 96, 128}, cout % 8 == 0, cout <= 256.
 int launch_linear_narrow(const void* x, const void* w, const float* bias, int64_t n, int cin, int cout, int act, void* out,
                          cudaStream_t stream) {
-  switch (cin / 16) {
-    case 1: return launch_narrow_ks<1>(x, w, bias, n, cout, act, out, stream);
-    case 2: return launch_narrow_ks<2>(x, w, bias, n, cout, act, out, stream);
-    case 3: return launch_narrow_ks<3>(x, w, bias, n, cout, act, out, stream);
-    case 4: return launch_narrow_ks<4>(x, w, bias, n, cout, act, out, stream);
-    case 5: return launch_narrow_ks<5>(x, w, bias, n, cout, act, out, stream);
-    case 6: return launch_narrow_ks<6>(x, w, bias, n, cout, act, out, stream);
-    case 7: return launch_narrow_ks<7>(x, w, bias, n, cout, act, out, stream);
-    case 8: return launch_narrow_ks<8>(x, w, bias, n, cout, act, out, stream);
+  switch (cin / 32) {
+    case 1: return launch_narrow_kb<1>(x, w, bias, n, cout, act, out, stream);
+    case 2: return launch_narrow_kb<2>(x, w, bias, n, cout, act, out, stream);
+    case 3: return launch_narrow_kb<3>(x, w, bias, n, cout, act, out, stream);
+    case 4: return launch_narrow_kb<4>(x, w, bias, n, cout, act, out, stream);
     default: return SS_BAD_ARGS;
   }
 }
