@@ -556,7 +556,8 @@ def lang_head_accumulate(feat, text, probs_accum, idx=None, normalize=False, imp
     n, c = feat.shape
     if impl == "tc" or (impl == "auto" and _head_tc_ok(feat, text)):
         fb = _head_operand(feat, normalize)
-        L.call("ss_lang_head_tc", L.ptr(fb), L.ptr(text.contiguous().to(_BF16)), n, c, text.shape[0], 0.0, 1,
+        tb = text.contiguous().to(_BF16)  # (bound to a name: the temporary must outlive the call's argument list)
+        L.call("ss_lang_head_tc", L.ptr(fb), L.ptr(tb), n, c, text.shape[0], 0.0, 1,
                L.ptr(idx), None, None, L.ptr(probs_accum), L.stream(), meta=dict(flops=2.0 * n * c * text.shape[0]))
         return probs_accum
     text = text.contiguous().float()
