@@ -38,9 +38,8 @@ constexpr int kG3Threads = 480;
 #define SS_G3_RED_WARPS 12
 #endif
 constexpr int kG3RedWarps = SS_G3_RED_WARPS;      // reducer warps of the fused kernel (warps 16..27; warp 15 idles)
-constexpr int kG3FusedThreads = 512 + 32 * kG3RedWarps;
-// register budget per thread of the fused kernel (setmaxnreg, by warpgroup): 8 epilogue warps x 88, 4 gather warps x 48,
-// 4 producer / issuer / relay warps x 40, 12 reducer warps x 80 = 64,512 of the SM's 65,536
+constexpr int kG3FusedThreads = 512 + 32 * kG3RedWarps;  // 896 threads x 72 registers (re-dividing the registers between the
+// roles with setmaxnreg -- 88 / 48 / 40 / 80 -- measured slower: the gather warps spill; profiles/r2_conv.md)
 constexpr int kG3BK = 64;
 constexpr int kG3SA = 7;  // A ring (gathered rows: ~3 us of latency under load, so as many bytes in flight as fit)
 constexpr int kG3SW = 4;  // W ring (TMA: a quarter of that latency)
@@ -97,31 +96,18 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
 #ifndef SS_G3_LAG_MB
 #define SS_G3_LAG_MB 32
 #endif
-#ifndef SS_G3_SETMAXNREG
-#define SS_G3_SETMAXNREG 0
-#endif
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() {
-#if SS_G3_SETMAXNREG
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-#endif
-}
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() {
-#if SS_G3_SETMAXNREG
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-#endif
-}
-
 // J = 0: products only.  J = 1..4 (= ceil(cout / 256)): FUSED gather-sum + LN + residual + LN.  Twelve more warps per CTA
-// (registers re-divided between the roles with setmaxnreg) walk the output voxels in serialized order, 32 consecutive
-// ranks per grab of a global counter (the order the pair rows of every tap follow), wait until the <= 27 product
-// tiles the voxel needs have been stored (per-tile counters, release / acquire), sum the rows and finish the Block's
-// LN(cpe) + residual + LN(norm1) (conv_reduce.cuh).  The tiles are processed in the order of their first output's rank
-// (tile_order) instead of tap by tap, so the reducers trail the GEMM front by a few tiles: the bf16 products are read
-// back from L2 instead of making a 2 x 3 GB round trip through HBM (dec0), the gathered input rows of the 27 taps of a
-// region are L2 hits, and the gather-sum pass (1.03 ms at dec0) runs under the MMAs.  GEMM roles never wait for
-// reducers and every CTA of the persistent grid is resident (1 per SM), so the waits cannot deadlock.
+// walk the output voxels along the serialized order the pair rows of every tap follow (ranks w, w + W, ..: W = all reducer
+// warps of the grid), wait until the <= 27 product tiles the voxel needs have been stored (per-tile counters: release
+// reductions by the epilogue warps, acquire loads here, prefetched one voxel ahead), sum the rows and finish the Block's
+// LN(cpe) + residual + LN(norm1) (conv_reduce.cuh).  The GEMM takes the tiles in the order of their first output's rank
+// (tile_order, exact: ss_kmap_pairs) instead of tap by tap and stays at most lag_tiles (~32 MB of products) ahead of the
+// reducers' front, so the bf16 products are read back from L2 instead of from HBM (dec0: DRAM reads 7.0 -> 3.8 GB) and
+// most of the gather-sum pass (1.03 ms at dec0) runs under the MMAs (2.90 -> 2.62 ms).
+// Deadlock freedom: reducers wait only for tiles; a tile a reducer waits for is below the front that reducer has
+// posted, so the GEMM may start it, and a CTA pair's earlier items are earlier in the order; every CTA of the
+// persistent grid is resident (1 per SM) or becomes resident without help from this kernel.  All spin waits are bounded
+// (4 s, trap).
 template <int J>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(J > 0 ? kG3FusedThreads : kG3Threads, 1)
 gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __restrict__ pair_in,
@@ -171,7 +157,6 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8 && warp < 12) {
-    if constexpr (FUSE) setmaxnreg_dec<48>();
     // ------------------------------------------------------------------ A gather: 128 threads, this CTA's 128 rows
     const int tid = threadIdx.x - 256;      // 0..127
     const int sub = tid >> 3, c = tid & 7;  // 8 lanes cover one 128-byte row segment
@@ -214,7 +199,6 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
     }
   } else if (warp >= 12 && warp < 16) {
     // W producer, MMA issuer, relay (and an idle warp in the fused kernel): one warpgroup, one register budget
-    if constexpr (FUSE) setmaxnreg_dec<40>();
     if (warp == 12) {
     // ------------------------------------------------------------------ W producer (TMA, one lane, both CTAs)
     if (lane == 0) {
@@ -276,7 +260,6 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
     }
     }
   } else if (warp < 8) {
-    if constexpr (FUSE) setmaxnreg_inc<88>();
     // ------------------------------------------------------------------ epilogue warps 0..7: (row quarter, column half)
     uint8_t* stg = smem + S::kOffEpi + warp * 2048;
     const int quarter = warp & 3, half = warp >> 2;
@@ -322,7 +305,6 @@ gather_gemm_pair_kernel(const __nv_bfloat16* __restrict__ X, const int32_t* __re
       }
     }
   } else if (FUSE && warp >= 16) {
-    if constexpr (FUSE) setmaxnreg_inc<80>();
     // ------------------------------------------------------------------ reducers: one warp per output voxel, in rank order
     constexpr int JJ = FUSE ? J : 1;
     constexpr int RR = JJ >= 3 ? 2 : 4;  // product rows in flight per lane (80 registers per thread)
