@@ -340,11 +340,14 @@ def test_linear_residual_cta_pair(n, cin, cout, inplace):
 
 
 @pytest.mark.parametrize("n,cin,cout", [(1, 16, 32), (255, 48, 96), (257, 64, 256), (1000, 768, 3072), (5001, 3072, 768),
-                                        (70001, 512, 2048)])
+                                        (70001, 512, 2048),
+                                        # cin = 32: the row-streaming warp-MMA kernel (csrc/gemm_narrow.cu), incl. a strip
+                                        # tail, one / two 128-column passes and a partial second pass
+                                        (1, 32, 32), (255, 32, 96), (70001, 32, 128), (4099, 32, 256), (300, 32, 160)])
 @pytest.mark.parametrize("act", [0, 1])
 def test_linear_act_cta_pair(n, cin, cout, act):
-    """csrc/gemm2cta.cu (tcgen05 cta_group::2, fused bias + exact GELU) vs float64 on the same bf16 operands, incl. row /
-    column / K tails.  bf16 output of an fp32 accumulation: |err| <= 2^-8 |want| + 1e-3 * sqrt(cin) * 2^-8 (accumulation
+    """csrc/gemm2cta.cu (tcgen05 cta_group::2, fused bias + exact GELU; cin = 32: csrc/gemm_narrow.cu) vs float64 on the
+    same bf16 operands, incl. row / column / K tails.  bf16 output of an fp32 accumulation: |err| <= 2^-8 |want| + 1e-3 * sqrt(cin) * 2^-8 (accumulation
     order), and relative L2 < 4e-3."""
     from scenesplat_b200 import ops
     torch.manual_seed(n + cin)
