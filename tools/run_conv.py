@@ -3,7 +3,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from scenesplat_b200 import ops, synthetic
+from scenesplat_b200 import ops, synthetic, _lib
+if os.environ.get("SS_LIB"):  # A/B against a variant build of the library (developer tool only)
+    _lib.LIB_PATH = os.path.abspath(os.environ["SS_LIB"])
 from oracle import gridsample as ogs, serialization as oser
 
 n_raw = int(os.environ.get("CONV_NRAW", 360000))
