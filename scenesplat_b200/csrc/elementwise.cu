@@ -138,7 +138,7 @@ template <typename TD, typename TN, int TPR, int NCH>
 __global__ void __launch_bounds__(256)
 add_layernorm_vec_kernel(const float* res, const TD* __restrict__ delta, const float* __restrict__ g0,
                          const float* __restrict__ b0, const float* __restrict__ g1, const float* __restrict__ b1,
-                         float eps, int64_t n, int C, float* res_out, TN* __restrict__ norm_out) {
+                         float eps, int64_t n, int C, float* res_out, TN* __restrict__ norm_out, float l2_eps = 0.f) {
   constexpr int RPW = 32 / TPR;  // rows per warp
   const int lane = threadIdx.x & 31, t = lane % TPR, sub = lane / TPR;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -215,6 +215,13 @@ add_layernorm_vec_kernel(const float* res, const TD* __restrict__ delta, const f
           }
         }
         rstd = rsqrtf(group_sum<TPR>(q) * invC + eps);
+      } else if (l2_eps > 0.f) {  // F.normalize(y, p=2, dim=1, eps): y / max(|y|_2, eps)
+        float q = 0.f;
+#pragma unroll
+        for (int u = 0; u < NCH; ++u)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) q += v[u][e] * v[u][e];  // (lanes past C hold zeros)
+        rstd = 1.f / fmaxf(sqrtf(group_sum<TPR>(q)), l2_eps);
       }
 #pragma unroll
       for (int u = 0; u < NCH; ++u) {
@@ -229,7 +236,7 @@ add_layernorm_vec_kernel(const float* res, const TD* __restrict__ delta, const f
             for (int e = 0; e < 8; ++e) o[e] = (v[u][e] - mean) * rstd * gg[e] + bb[e];
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = v[u][e];
+            for (int e = 0; e < 8; ++e) o[e] = v[u][e] * rstd;  // (rstd = 1 unless L2-normalising)
           }
           st8(norm_out + (size_t)r * C + c * 8, o);
         }
@@ -360,6 +367,46 @@ int ss_add_layernorm(const float* res, const void* delta, int delta_is_bf16, con
   else SS_LN_V_(float, float);
 #undef SS_LN_V_
 #undef SS_LN_
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+// out = F.normalize(res + delta, p=2, dim=1, eps) in one pass: the last Block's residual add fused with the L2 normalisation
+// LangPretrainer applies to the backbone output (models/default.py:98); neither the un-normalised sum nor a bf16 copy is
+// written.  channels % 8 == 0, <= 1024, 16-byte aligned pointers.
+int ss_add_l2_normalize(const float* res, const void* delta, int delta_is_bf16, float eps, int64_t n, int channels,
+                        float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || channels < 8 || channels % 8 != 0 || channels > 1024 || !(eps > 0.f)) return SS_BAD_ARGS;
+  if (n == 0) return SS_OK;
+  if (!res || !delta || !out) return SS_BAD_ARGS;
+  if ((((uintptr_t)res | (uintptr_t)delta | (uintptr_t)out) % 16) != 0) return SS_BAD_ARGS;
+  const int nchunk = channels / 8;
+  int tpr = 1;
+  while (tpr < 32 && tpr < nchunk) tpr <<= 1;
+  const int nch = (nchunk + tpr - 1) / tpr;
+  const int rpw = 32 / tpr;
+  const int vblocks = (int)ss::imin64(ss::ceil_div64(n, 8 * rpw), 16 * ss::kNumSMs);
+#define SS_L2_(TD, T, N)                                                                                            \
+  ss::add_layernorm_vec_kernel<TD, float, T, N><<<vblocks, 256, 0, stream>>>(res, (const TD*)delta, nullptr, nullptr,   \
+                                                                             nullptr, nullptr, 0.f, n, channels, nullptr, \
+                                                                             out, eps)
+#define SS_L2_T_(TD)                       \
+  do {                                     \
+    if (tpr == 1) SS_L2_(TD, 1, 1);        \
+    else if (tpr == 2) SS_L2_(TD, 2, 1);   \
+    else if (tpr == 4) SS_L2_(TD, 4, 1);   \
+    else if (tpr == 8) SS_L2_(TD, 8, 1);   \
+    else if (tpr == 16) SS_L2_(TD, 16, 1); \
+    else if (nch == 1) SS_L2_(TD, 32, 1);  \
+    else if (nch == 2) SS_L2_(TD, 32, 2);  \
+    else if (nch == 3) SS_L2_(TD, 32, 3);  \
+    else SS_L2_(TD, 32, 4);                \
+  } while (0)
+  if (delta_is_bf16) SS_L2_T_(__nv_bfloat16);
+  else SS_L2_T_(float);
+#undef SS_L2_T_
+#undef SS_L2_
   SS_CHECK_LAUNCH();
   return SS_OK;
 }

@@ -144,6 +144,8 @@ class LangPretrainer(nn.Module):
 
     def _features(self, input_dict):
         point = Point(input_dict)
+        if not (torch.is_grad_enabled() and self.training) and self._fused_normalize():
+            return self.features_prepared(self.backbone.prepare(point))
         point_feat = self.backbone(point)
         if point_feat["feat"].requires_grad:  # training: torch operator under autograd
             point_feat["feat"] = F.normalize(point_feat["feat"].float(), p=2, dim=1)
@@ -151,14 +153,20 @@ class LangPretrainer(nn.Module):
             point_feat["feat"] = ops.l2_normalize(point_feat["feat"], eps=1e-12)  # F.normalize(p=2, dim=1), default.py:98
         return point_feat
 
+    def _fused_normalize(self):
+        """The backbone can write F.normalize(feat) from its last Block (PointTransformerV3.run(l2_normalize=True))."""
+        run = getattr(self.backbone, "run", None)
+        return run is not None and hasattr(self.backbone, "prepare") and "l2_normalize" in run.__code__.co_varnames
+
     def prepare(self, input_dict):
         """Index phase (serialization, pooling levels, kernel maps; all host syncs) -> prepared Point."""
         return self.backbone.prepare(Point(input_dict))
 
     def features_prepared(self, point):
         """Feature phase on a prepared Point (eval): L2-normalised point features, no host sync."""
-        point_feat = self.backbone.run(point)
-        point_feat["feat"] = ops.l2_normalize(point_feat["feat"], eps=1e-12)
+        point_feat = self.backbone.run(point, l2_normalize=True) if self._fused_normalize() else self.backbone.run(point)
+        if not point_feat.pop("_l2_normalized", False):
+            point_feat["feat"] = ops.l2_normalize(point_feat["feat"], eps=1e-12)
         return point_feat
 
     def forward(self, input_dict, chunk_size=None):

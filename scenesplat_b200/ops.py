@@ -443,6 +443,16 @@ def add_layernorm(res, delta, ln0=None, ln1=None, eps=1e-5, want_res=True, norm_
     return res_out, norm_out
 
 
+def add_l2_normalize(res_f32, delta, eps=1e-12):
+    """F.normalize(res + delta, p=2, dim=1, eps) in one pass (fp32 out): the backbone's last residual add fused with
+    LangPretrainer's normalisation."""
+    n, c = res_f32.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=res_f32.device)
+    L.call("ss_add_l2_normalize", L.ptr(res_f32), L.ptr(delta), _isbf(delta), float(eps), n, c, L.ptr(out), L.stream(),
+           meta=dict(bytes=float(n * c * (8 + delta.element_size()))))
+    return out
+
+
 def subm_conv_wgrad(x_bf16, dy_bf16, pairs, pair_out, k3, rows_per_chunk=8192):
     """-> dw fp32 [k3, cout, cin] = per-tap dY[pair_out]^T X[pair_in] on the tensor cores (split-K over pair chunks)."""
     cin, cout = x_bf16.shape[1], dy_bf16.shape[1]

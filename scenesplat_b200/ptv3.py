@@ -28,7 +28,7 @@ import torch.nn.functional as F
 from . import _lib as L
 from . import ops
 from . import spconv_compat as spconv
-from .modules import PointModule, PointSequential
+from .modules import PointModule, PointSequential, _apply
 from .registry import MODELS
 from .structure import Dict, Point, offset2bincount
 
@@ -329,6 +329,14 @@ class Block(PointModule):
         # (MLP.forward_residual -- fc2 with the residual add in its epilogue -- is built and tested but measured SLOWER
         # than GEMM + this add pass at every Block shape: 1.43 vs 1.37 ms at dec0, profiles/r2_gemm.md)
         m = self.mlp[0](h)
+        if point.pop("_emit_l2_normalized", False) and x.shape[1] % 8 == 0 and x.shape[1] <= 1024:
+            # last Block of the backbone under LangPretrainer (eval): residual add + F.normalize(p=2, dim=1) in one pass;
+            # neither the un-normalised sum nor its bf16 copy is written (models/default.py:98)
+            x = ops.add_l2_normalize(x, m, eps=1e-12)
+            point.feat = x
+            point["_l2_normalized"] = True
+            point.sparse_conv_feat = point.sparse_conv_feat.replace_feature(x)
+            return point
         x, xb = ops.add_layernorm(x, m, None, None, norm_dtype=BF16, inplace=True)
         point.feat = x
         point["_bf16_shadow"] = (x, xb)
@@ -621,12 +629,22 @@ class PointTransformerV3(PointModule):
         self.plan_indices(point)
         return point
 
-    def run(self, point):
-        """Feature phase of a forward on a prepared Point: no host sync."""
+    def run(self, point, l2_normalize=False):
+        """Feature phase of a forward on a prepared Point: no host sync.  l2_normalize (LangPretrainer, eval): the last
+        decoder Block writes F.normalize(feat, p=2, dim=1) instead of feat and marks the Point `_l2_normalized`."""
         point = self.embedding(point)
         point = self.enc(point)
         if not self.cls_mode:
-            point = self.dec(point)
+            stages = list(self.dec.children())
+            for i, stage in enumerate(stages):
+                if l2_normalize and i == len(stages) - 1:
+                    mods = list(stage.children())
+                    for j, m in enumerate(mods):
+                        if j == len(mods) - 1 and isinstance(m, Block):
+                            point["_emit_l2_normalized"] = True
+                        point = _apply(m, point)
+                else:
+                    point = stage(point)
         return point
 
     def forward(self, data_dict):

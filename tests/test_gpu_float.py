@@ -363,3 +363,20 @@ def test_linear_act_cta_pair(n, cin, cout, act):
     assert float(err.norm() / want.norm()) < 4e-3
     nob = ops.linear_act(x.cuda(), w.cuda(), None, 0).float().cpu()          # bias is optional
     assert float((nob.double() - x.double() @ w.double().t()).abs().max()) <= 2.0 ** -7 * float(want.abs().max()) + 2e-3
+
+
+@pytest.mark.parametrize("n,c,bf", [(1, 8, True), (1000, 768, True), (777, 256, False), (33, 40, True)])
+def test_add_l2_normalize(n, c, bf):
+    """ss_add_l2_normalize = F.normalize(res + delta, p=2, dim=1, eps=1e-12) in one pass (fp32): 2e-6 relative (the sum
+    of squares is a warp-shuffle tree instead of torch's order; one reciprocal instead of a division)."""
+    from scenesplat_b200 import ops
+    torch.manual_seed(n + c)
+    res = torch.randn(n, c).cuda() * 3
+    delta = torch.randn(n, c).cuda()
+    if bf:
+        delta = delta.bfloat16()
+    want = F.normalize(res + delta.float(), p=2, dim=1, eps=1e-12)
+    got = ops.add_l2_normalize(res, delta, eps=1e-12)
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=2e-6, atol=1e-7)
+    zero = ops.add_l2_normalize(torch.zeros(4, c).cuda(), torch.zeros(4, c).cuda().bfloat16(), eps=1e-12)
+    assert float(zero.abs().max()) == 0.0  # eps guards the zero row, as in F.normalize
