@@ -155,8 +155,7 @@ class LangPretrainer(nn.Module):
 
     def _fused_normalize(self):
         """The backbone can write F.normalize(feat) from its last Block (PointTransformerV3.run(l2_normalize=True))."""
-        run = getattr(self.backbone, "run", None)
-        return run is not None and hasattr(self.backbone, "prepare") and "l2_normalize" in run.__code__.co_varnames
+        return bool(getattr(self.backbone, "fused_l2_normalize", False))
 
     def prepare(self, input_dict):
         """Index phase (serialization, pooling levels, kernel maps; all host syncs) -> prepared Point."""

@@ -629,6 +629,8 @@ class PointTransformerV3(PointModule):
         self.plan_indices(point)
         return point
 
+    fused_l2_normalize = True  # run(point, l2_normalize=True) exists (LangPretrainer asks for it in eval mode)
+
     def run(self, point, l2_normalize=False):
         """Feature phase of a forward on a prepared Point: no host sync.  l2_normalize (LangPretrainer, eval): the last
         decoder Block writes F.normalize(feat, p=2, dim=1) instead of feat and marks the Point `_l2_normalized`."""
