@@ -1,6 +1,7 @@
-// Kernel map (neighbour table) of a submanifold k^3 convolution, built from the SORTED serialization
-// keys: every voxel looks its neighbours up by binary search in the sorted code row it already has
-// (no hash table).  Only half of the taps are searched; the mirrored tap is filled through the
+// Kernel map (neighbour table) of a submanifold k^3 convolution, built from the serialization codes the Point
+// already has: the codes go into an open-addressing table in the workspace (one CAS per voxel), every voxel then
+// looks its neighbours' codes up (1 - 2 probes of 16 bytes each; round 1 - 2 searched the sorted row: 19 dependent
+// loads per lookup).  Only half of the taps are searched; the mirrored tap is filled through the
 // symmetry nbr[t][p] = q  <=>  nbr[k^3-1-t][q] = p.
 //
 // Replaces (reference): the indice-pair build inside spconv.SubMConv3d
@@ -11,29 +12,59 @@
 
 namespace ss {
 
-__global__ void __launch_bounds__(256)
-sorted_keys_kernel(const int64_t* __restrict__ code, const int64_t* __restrict__ order, int64_t n,
-                   uint64_t* __restrict__ skeys) {
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
-    skeys[j] = (uint64_t)code[order[j]];
+// Open-addressing table of the active voxels: 16-byte entries {key, voxel}, linear probing, at most half full.
+// Equal keys (not produced by GridSample, but legal input) keep the SMALLEST voxel index: what a lower-bound search
+// in a stably sorted row returns.
+struct __align__(16) KmapSlot {
+  unsigned long long key;
+  unsigned int voxel;
+  unsigned int pad;
+};
+constexpr unsigned long long kKmapEmpty = ~0ull;  // codes use at most 48 + batch bits
+
+inline int64_t kmap_table_slots(int64_t n) {
+  int64_t s = 1024;
+  while (s < 2 * n) s <<= 1;
+  return s;
+}
+inline size_t kmap_table_bytes(int64_t n) { return align_up((size_t)kmap_table_slots(n > 0 ? n : 1) * sizeof(KmapSlot), 256); }
+
+__device__ __forceinline__ uint32_t kmap_hash(uint64_t key, int shift) {
+  return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> shift);
 }
 
+__global__ void __launch_bounds__(256)
+kmap_insert_kernel(const int64_t* __restrict__ code, int64_t n, KmapSlot* __restrict__ table, int shift, uint32_t mask) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const unsigned long long key = (unsigned long long)code[p];
+  uint32_t slot = kmap_hash(key, shift);
+  while (true) {
+    const unsigned long long old = atomicCAS(&table[slot].key, kKmapEmpty, key);
+    if (old == kKmapEmpty || old == key) {
+      atomicMin(&table[slot].voxel, (unsigned int)p);
+      return;
+    }
+    slot = (slot + 1u) & mask;
+  }
+}
+
+// One thread per voxel p (coalesced coordinate reads and direct-tap writes); the lower half of the taps is looked up,
+// the mirrored tap is written at the neighbour.
 template <typename CoordT>
 __global__ void __launch_bounds__(256)
 kmap_search_kernel(const CoordT* __restrict__ grid_coord, const int64_t* __restrict__ batch,
-                   const int64_t* __restrict__ order, const uint64_t* __restrict__ skeys, int64_t n, int depth,
+                   const KmapSlot* __restrict__ table, int shift, uint32_t mask, int64_t n, int depth,
                    int order_id, int k, int32_t* __restrict__ nbr, unsigned long long* __restrict__ tap_count) {
   extern __shared__ unsigned int s_cnt[];  // [k^3 / 2]
   const int k3 = k * k * k, half = k3 / 2, r = k / 2;
   for (int i = threadIdx.x; i < half; i += blockDim.x) s_cnt[i] = 0u;
   __syncthreads();
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = j < n;
-  int64_t p = 0;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = p < n;
   int x = 0, y = 0, z = 0;
   uint64_t bpart = 0;
   if (active) {
-    p = order[j];
     x = (int)grid_coord[p * 3 + 0];
     y = (int)grid_coord[p * 3 + 1];
     z = (int)grid_coord[p * 3 + 2];
@@ -41,6 +72,7 @@ kmap_search_kernel(const CoordT* __restrict__ grid_coord, const int64_t* __restr
     nbr[(size_t)half * n + p] = (int32_t)p;  // centre tap
   }
   const int lim = 1 << depth;
+  const uint4* slots = reinterpret_cast<const uint4*>(table);
   for (int t = 0; t < half; ++t) {
     const int dx = t / (k * k) - r, dy = (t / k) % k - r, dz = t % k - r;
     int32_t found = -1;
@@ -48,12 +80,17 @@ kmap_search_kernel(const CoordT* __restrict__ grid_coord, const int64_t* __restr
       const int qx = x + dx, qy = y + dy, qz = z + dz;
       if (qx >= 0 && qy >= 0 && qz >= 0 && qx < lim && qy < lim && qz < lim) {
         const uint64_t key = bpart | sfc_key(order_id, (uint32_t)qx, (uint32_t)qy, (uint32_t)qz, depth);
-        int64_t lo = 0, hi = n;
-        while (lo < hi) {
-          const int64_t mid = (lo + hi) >> 1;
-          if (skeys[mid] < key) lo = mid + 1; else hi = mid;
+        uint32_t slot = kmap_hash(key, shift);
+        while (true) {
+          const uint4 e = __ldg(slots + slot);
+          const uint64_t ek = ((uint64_t)e.y << 32) | e.x;
+          if (ek == key) {
+            found = (int32_t)e.z;
+            break;
+          }
+          if (ek == kKmapEmpty) break;
+          slot = (slot + 1u) & mask;
         }
-        if (lo < n && skeys[lo] == key) found = (int32_t)order[lo];
       }
       nbr[(size_t)t * n + p] = found;
       if (found >= 0) nbr[(size_t)(k3 - 1 - t) * n + found] = (int32_t)p;
@@ -105,11 +142,15 @@ struct PairRuns {
 };
 
 // Order of the product tiles for the fused conv: position of tile t = number of tiles with a smaller (first rank, index)
-// key.  T is a few thousand (7.6 k at the benchmark chunk): T^2 comparisons from shared-memory chunks, no sort.
+// key.  T is a few thousand (7.6 k at the benchmark chunk): T^2 comparisons from shared-memory chunks, no sort.  Eight
+// lanes share one tile (each takes every eighth candidate; a warp reads eight distinct words per step, broadcast to its
+// four tiles), so T / 32 CTAs are in flight instead of T / 256 (30 CTAs at the benchmark chunk: 111 us for 58 M compares).
+constexpr int kRankLanes = 8;
+constexpr int kRankTilesPerCta = 256 / kRankLanes;
 __global__ void __launch_bounds__(256) tile_rank_kernel(const int32_t* __restrict__ first_rank, int tiles,
                                                         int32_t* __restrict__ tile_order, int32_t* __restrict__ tile_pos) {
   __shared__ int32_t s_fr[1024];
-  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int t = blockIdx.x * kRankTilesPerCta + (int)(threadIdx.x / kRankLanes), part = (int)(threadIdx.x % kRankLanes);
   const int32_t mine = t < tiles ? first_rank[t] : 0;
   int pos = 0;
   for (int base = 0; base < tiles; base += 1024) {
@@ -117,12 +158,15 @@ __global__ void __launch_bounds__(256) tile_rank_kernel(const int32_t* __restric
     __syncthreads();
     for (int i = threadIdx.x; i < m; i += 256) s_fr[i] = first_rank[base + i];
     __syncthreads();
-    for (int i = 0; i < m; ++i) {
+#pragma unroll 8
+    for (int i = part; i < m; i += kRankLanes) {
       const int32_t v = s_fr[i];
       pos += (v < mine || (v == mine && base + i < t)) ? 1 : 0;
     }
   }
-  if (t < tiles) {
+#pragma unroll
+  for (int o = kRankLanes / 2; o; o >>= 1) pos += __shfl_xor_sync(0xffffffffu, pos, o);
+  if (part == 0 && t < tiles) {
     tile_pos[t] = pos;
     tile_order[pos] = t;
   }
@@ -134,7 +178,7 @@ extern "C" {
 
 size_t ss_kmap_workspace_bytes(int64_t n, int k) {
   if (n < 0 || k < 1) return 0;
-  return ss::align_up((size_t)(n > 0 ? n : 1) * 8, 256) + ss::align_up(ss::runs_workspace_bytes(n, k * k * k), 256) + 512;
+  return ss::kmap_table_bytes(n) + ss::align_up(ss::runs_workspace_bytes(n, k * k * k), 256) + 512;
 }
 
 int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* batch, const int64_t* code_row,
@@ -150,19 +194,25 @@ int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* bat
   if (!grid_coord || !batch || !code_row || !order_row || !nbr || !workspace) return SS_BAD_ARGS;
   if (workspace_bytes < ss_kmap_workspace_bytes(n, k) - 512) return SS_BAD_ARGS;
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  uint64_t* skeys = (uint64_t*)ws;
+  ss::KmapSlot* table = (ss::KmapSlot*)ws;
+  const int64_t slots = ss::kmap_table_slots(n);
+  int log2s = 0;
+  while ((1ll << log2s) < slots) ++log2s;
+  const int shift = 64 - log2s;
+  const uint32_t mask = (uint32_t)(slots - 1);
   const int blocks = ss::ceil_div((int)n, 256);
-  ss::sorted_keys_kernel<<<min(blocks, 16 * ss::kNumSMs), 256, 0, stream>>>(code_row, order_row, n, skeys);
+  SS_CUDA(cudaMemsetAsync(table, 0xff, (size_t)slots * sizeof(ss::KmapSlot), stream));
+  ss::kmap_insert_kernel<<<blocks, 256, 0, stream>>>(code_row, n, table, shift, mask);
   SS_CHECK_LAUNCH();
   // mirrored half (taps > centre) is only written where a neighbour exists
   SS_CUDA(cudaMemsetAsync(nbr + (size_t)(k3 / 2 + 1) * n, 0xff, (size_t)(k3 / 2) * n * 4, stream));
   const size_t smem = (size_t)(k3 / 2) * 4;
   if (coord_is_int32)
-    ss::kmap_search_kernel<int><<<blocks, 256, smem, stream>>>((const int*)grid_coord, batch, order_row, skeys, n, depth,
+    ss::kmap_search_kernel<int><<<blocks, 256, smem, stream>>>((const int*)grid_coord, batch, table, shift, mask, n, depth,
                                                               order_id, k, nbr, (unsigned long long*)tap_count_dev);
   else
-    ss::kmap_search_kernel<long long><<<blocks, 256, smem, stream>>>((const long long*)grid_coord, batch, order_row, skeys,
-                                                                    n, depth, order_id, k, nbr,
+    ss::kmap_search_kernel<long long><<<blocks, 256, smem, stream>>>((const long long*)grid_coord, batch, table, shift,
+                                                                    mask, n, depth, order_id, k, nbr,
                                                                     (unsigned long long*)tap_count_dev);
   SS_CHECK_LAUNCH();
   ss::kmap_center_count<<<1, 32, 0, stream>>>((unsigned long long*)tap_count_dev, k3 / 2, n);
@@ -185,12 +235,12 @@ int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k
   SS_CUDA(cudaMemsetAsync(pair_in, 0, (size_t)p_pad * 4, stream));
   if (workspace_bytes < ss_kmap_workspace_bytes(n, k) - 512) return SS_BAD_ARGS;
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  ws += ss::align_up((size_t)n * 8, 256);
+  ws += ss::kmap_table_bytes(n);
   ss::PairRuns f{nbr, order_row, tap_base_dev, n, pair_in, ypos, ypos_rank, tile_first_rank};
   int rc = ss::runs_launch(f, n, ws, nullptr, stream, k * k * k);
   if (rc != SS_OK || !tile_order || p_pad == 0) return rc;
   const int tiles = (int)(p_pad / 256);
-  ss::tile_rank_kernel<<<ss::ceil_div(tiles, 256), 256, 0, stream>>>(tile_first_rank, tiles, tile_order, tile_pos);
+  ss::tile_rank_kernel<<<ss::ceil_div(tiles, ss::kRankTilesPerCta), 256, 0, stream>>>(tile_first_rank, tiles, tile_order, tile_pos);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }
