@@ -141,6 +141,113 @@ struct PairRuns {
   __device__ void finish(int, uint32_t) const {}
 };
 
+// The same pair lists for k = 3 in ONE pass over the ranks: a thread takes four ranks j and all 27 taps of each (PairRuns
+// above walks one (tap, rank) per thread: 27 reads of order[j], 27 four-byte writes into every 128-byte line of ypos_rank and a
+// memset of that table before).  Tiles of 1024 ranks are taken in ticket order; a tile publishes its 27 tap counts in one
+// 128-byte status line and reads the lines of all earlier tiles in parallel (warp = tile, lane = tap): no chained look-back.
+// ypos_rank rows leave through a per-warp shared-memory transposition as full 128-byte lines (columns 27..31 = -1).
+constexpr int kPairThreads = 256;
+constexpr int kPairItems = 4;
+constexpr int kPairTile = kPairThreads * kPairItems;
+inline size_t pair27_workspace_bytes(int64_t n) { return 256 + (size_t)ceil_div64(n > 0 ? n : 1, kPairTile) * 128; }
+
+__global__ void __launch_bounds__(kPairThreads, 2)
+pair27_kernel(const int32_t* __restrict__ nbr, const int64_t* __restrict__ order, const int64_t* __restrict__ tap_base,
+              int64_t n, uint32_t* counter, uint32_t* status, int32_t* __restrict__ pair_in, int32_t* __restrict__ ypos,
+              int32_t* __restrict__ ypos_rank, int32_t* __restrict__ tile_first_rank) {
+  constexpr int K3 = 27, W = kPairThreads / 32;
+  __shared__ uint32_t s_cnt[kPairItems * W][K3];  // ballot totals per (item, warp), then their exclusive scan per tap
+  __shared__ uint32_t s_part[W][32];
+  __shared__ uint32_t s_before[32];
+  __shared__ int32_t s_base[K3];
+  __shared__ int32_t s_tr[W][32][33];
+  __shared__ int s_ticket;
+  if (threadIdx.x == 0) s_ticket = (int)atomicAdd(counter, 1u);
+  if (threadIdx.x < K3) s_base[threadIdx.x] = (int32_t)tap_base[threadIdx.x];
+  __syncthreads();
+  const int tile = s_ticket, lane = (int)lane_id(), w = (int)(threadIdx.x >> 5);
+  const int64_t base = (int64_t)tile * kPairTile;
+  int32_t p[kPairItems];
+  uint32_t m[kPairItems];
+#pragma unroll
+  for (int i = 0; i < kPairItems; ++i) {
+    const int64_t j = base + i * kPairThreads + threadIdx.x;
+    p[i] = j < n ? (int32_t)order[j] : -1;
+    m[i] = 0u;
+  }
+#pragma unroll
+  for (int t = 0; t < K3; ++t) {
+#pragma unroll
+    for (int i = 0; i < kPairItems; ++i)
+      if (p[i] >= 0 && nbr[(size_t)t * n + p[i]] >= 0) m[i] |= 1u << t;
+  }
+#pragma unroll
+  for (int t = 0; t < K3; ++t) {
+#pragma unroll
+    for (int i = 0; i < kPairItems; ++i) {
+      const uint32_t b = __ballot_sync(0xffffffffu, (m[i] >> t) & 1u);
+      if (lane == 0) s_cnt[i * W + w][t] = (uint32_t)__popc(b);
+    }
+  }
+  __syncthreads();
+  if (w == 0) {  // lane = tap: exclusive scan over the tile's (item, warp) groups in rank order, publish the tile's count
+    uint32_t run = 0u;
+    if (lane < K3) {
+      for (int e = 0; e < kPairItems * W; ++e) {
+        const uint32_t c = s_cnt[e][lane];
+        s_cnt[e][lane] = run;
+        run += c;
+      }
+    }
+    st_volatile_u32(status + (size_t)tile * 32 + lane, kFlagAggregate | run);
+  }
+  uint32_t acc = 0u;
+  for (int tt = w; tt < tile; tt += W) {
+    uint32_t v;
+    while (((v = ld_volatile_u32(status + (size_t)tt * 32 + lane)) & kFlagAggregate) == 0u) {}
+    acc += v & kValueMask;
+  }
+  s_part[w][lane] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t sum = 0u;
+#pragma unroll
+    for (int ww = 0; ww < W; ++ww) sum += s_part[ww][threadIdx.x];
+    s_before[threadIdx.x] = sum;
+  }
+  __syncthreads();
+  const uint32_t lt = lanemask_lt();
+#pragma unroll
+  for (int i = 0; i < kPairItems; ++i) {
+    const int64_t j = base + i * kPairThreads + threadIdx.x;
+    const int32_t pi = p[i];
+    const uint32_t mi = m[i];
+#pragma unroll
+    for (int t = 0; t < K3; ++t) {
+      const bool bit = (mi >> t) & 1u;
+      const uint32_t b = __ballot_sync(0xffffffffu, bit);
+      const uint32_t run = s_before[t] + s_cnt[i * W + w][t] + (uint32_t)__popc(b & lt);
+      const int32_t pos = bit ? s_base[t] + (int32_t)run : -1;
+      if (pi >= 0) {
+        ypos[(size_t)t * n + pi] = pos;
+        if (bit) {
+          pair_in[pos] = nbr[(size_t)t * n + pi];
+          if (tile_first_rank && (run & 255u) == 0u) tile_first_rank[pos >> 8] = (int32_t)j;  // tap bases: multiples of 256
+        }
+      }
+      s_tr[w][lane][t] = pos;
+    }
+    if (ypos_rank) {
+#pragma unroll
+      for (int t = K3; t < 32; ++t) s_tr[w][lane][t] = -1;
+      __syncwarp();
+      const int64_t j0 = base + i * kPairThreads + w * 32;
+      for (int r = 0; r < 32 && j0 + r < n; ++r) ypos_rank[(j0 + r) * 32 + lane] = s_tr[w][r][lane];
+      __syncwarp();
+    }
+  }
+}
+
 // Order of the product tiles for the fused conv: position of tile t = number of tiles with a smaller (first rank, index)
 // key.  T is a few thousand (7.6 k at the benchmark chunk): T^2 comparisons from shared-memory chunks, no sort.  Eight
 // lanes share one tile (each takes every eighth candidate; a warp reads eight distinct words per step, broadcast to its
@@ -178,7 +285,8 @@ extern "C" {
 
 size_t ss_kmap_workspace_bytes(int64_t n, int k) {
   if (n < 0 || k < 1) return 0;
-  return ss::kmap_table_bytes(n) + ss::align_up(ss::runs_workspace_bytes(n, k * k * k), 256) + 512;
+  const size_t scan = ss::runs_workspace_bytes(n, k * k * k), pair27 = ss::pair27_workspace_bytes(n);
+  return ss::kmap_table_bytes(n) + ss::align_up(scan > pair27 ? scan : pair27, 256) + 512;
 }
 
 int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* batch, const int64_t* code_row,
@@ -229,15 +337,23 @@ int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k
   if (!nbr || !order_row || !tap_base_dev || !pair_in || !ypos || !workspace) return SS_BAD_ARGS;
   if ((ypos_rank && k != 3) || (tile_first_rank && p_pad % 256 != 0)) return SS_BAD_ARGS;
   if ((tile_order || tile_pos) && !(tile_first_rank && tile_order && tile_pos)) return SS_BAD_ARGS;
-  // columns 27..31 of the rank-major table stay -1
-  if (ypos_rank) SS_CUDA(cudaMemsetAsync(ypos_rank, 0xff, (size_t)n * 32 * 4, stream));
   // padding rows of every tap segment gather row 0 (their products are never read back)
   SS_CUDA(cudaMemsetAsync(pair_in, 0, (size_t)p_pad * 4, stream));
   if (workspace_bytes < ss_kmap_workspace_bytes(n, k) - 512) return SS_BAD_ARGS;
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   ws += ss::kmap_table_bytes(n);
-  ss::PairRuns f{nbr, order_row, tap_base_dev, n, pair_in, ypos, ypos_rank, tile_first_rank};
-  int rc = ss::runs_launch(f, n, ws, nullptr, stream, k * k * k);
+  int rc = SS_OK;
+  if (k == 3) {
+    SS_CUDA(cudaMemsetAsync(ws, 0, ss::pair27_workspace_bytes(n), stream));
+    const int ptiles = (int)ss::ceil_div64(n, ss::kPairTile);
+    ss::pair27_kernel<<<ptiles, ss::kPairThreads, 0, stream>>>(nbr, order_row, tap_base_dev, n, (uint32_t*)ws,
+                                                              (uint32_t*)(ws + 256), pair_in, ypos, ypos_rank,
+                                                              tile_first_rank);
+    SS_CHECK_LAUNCH();
+  } else {
+    ss::PairRuns f{nbr, order_row, tap_base_dev, n, pair_in, ypos, ypos_rank, tile_first_rank};
+    rc = ss::runs_launch(f, n, ws, nullptr, stream, k * k * k);
+  }
   if (rc != SS_OK || !tile_order || p_pad == 0) return rc;
   const int tiles = (int)(p_pad / 256);
   ss::tile_rank_kernel<<<ss::ceil_div(tiles, ss::kRankTilesPerCta), 256, 0, stream>>>(tile_first_rank, tiles, tile_order, tile_pos);
