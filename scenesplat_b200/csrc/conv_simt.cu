@@ -74,8 +74,12 @@ __global__ void __launch_bounds__(256)
 subm_conv_small_kernel(const TI* __restrict__ in, const int32_t* __restrict__ nbr, const float* __restrict__ wt,
                        const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                        int act, int64_t n, int k3, int cin_rt, int cout, TO* __restrict__ out) {
+  constexpr int CINP = (CIN + 3) / 4 * 4;
+  __shared__ float4 s_rows[8][32 * (CINP / 4)];  // per warp: the 32 voxels' input rows of the current tap
   const int cin = EXACT ? CIN : cin_rt;
   const int lane = threadIdx.x & 31;
+  const float4* warp_rows = s_rows[threadIdx.x >> 5];
+  float4* my_row = s_rows[threadIdx.x >> 5] + lane * (CINP / 4);
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t p0 = warp0 * 32; p0 < n; p0 += nwarp * 32) {
@@ -89,24 +93,40 @@ subm_conv_small_kernel(const TI* __restrict__ in, const int32_t* __restrict__ nb
       if (t + 1 < k3) q_next = p < n ? nbr[(size_t)(t + 1) * n + p] : -1;
       const uint32_t mask = __ballot_sync(0xffffffffu, q >= 0);
       if (mask == 0u) continue;
-      float x[CIN], w[CIN];
+      float x[CINP], w[CIN];
 #pragma unroll
-      for (int ci = 0; ci < CIN; ++ci) {
-        x[ci] = (q >= 0 && (EXACT || ci < cin)) ? cvt_in<TI>(in[(size_t)q * cin + ci]) : 0.f;
+      for (int ci = 0; ci < CINP; ++ci)
+        x[ci] = (ci < CIN && q >= 0 && (EXACT || ci < cin)) ? cvt_in<TI>(in[(size_t)q * cin + ci]) : 0.f;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
         w[ci] = ((EXACT || ci < cin) && lane < cout) ? __ldg(wt + ((size_t)t * cin + ci) * cout + lane) : 0.f;
+      // the lane's input row goes to shared memory; every lane then reads voxel i's row as broadcast 16-byte loads
+      // (3 LDS.128 per active (tap, voxel) pair instead of 11 SHFL: the shuffles bound the round-1 kernel)
+      if (q >= 0) {
+#pragma unroll
+        for (int c4 = 0; c4 < CINP / 4; ++c4)
+          my_row[c4] = make_float4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]);
       }
+      __syncwarp();
 #pragma unroll
       for (int g4 = 0; g4 < 8; ++g4) {
         if (((mask >> (4 * g4)) & 0xfu) == 0u) continue;  // warp-uniform
 #pragma unroll
         for (int i = 4 * g4; i < 4 * g4 + 4; ++i) {
           if ((mask >> i) & 1u) {
+            float xi[CINP];
+#pragma unroll
+            for (int c4 = 0; c4 < CINP / 4; ++c4) {
+              const float4 v = warp_rows[i * (CINP / 4) + c4];
+              xi[4 * c4] = v.x, xi[4 * c4 + 1] = v.y, xi[4 * c4 + 2] = v.z, xi[4 * c4 + 3] = v.w;
+            }
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
-              if (EXACT || ci < cin) acc[i] = fmaf(__shfl_sync(0xffffffffu, x[ci], i), w[ci], acc[i]);
+              if (EXACT || ci < cin) acc[i] = fmaf(xi[ci], w[ci], acc[i]);
           }
         }
       }
+      __syncwarp();
     }
     if (lane < cout) {
       const float b = bias ? bias[lane] : 0.f;
