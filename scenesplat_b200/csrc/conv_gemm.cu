@@ -208,6 +208,63 @@ conv_reduce_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __rest
   }
 }
 
+// The same gather-sum for narrow outputs (cout = 8 * LPV, LPV = 4 / 8 / 16 lanes per voxel): with one warp per voxel only
+// cout / 8 lanes carry data and every voxel pays 27 strided position loads of its own.  Here a warp takes 32 / LPV
+// CONSECUTIVE voxels: a tap's positions are one coalesced load for the whole warp, and every lane group walks its voxel's
+// active taps in ascending order (the summation order of conv_reduce_kernel: bit-identical output).
+template <typename TO, int LPV>
+__global__ void __launch_bounds__(256, 3)
+conv_reduce_narrow_kernel(const __nv_bfloat16* __restrict__ prod, const int32_t* __restrict__ ypos,
+                          const float* __restrict__ bias, int64_t n, int k3, TO* __restrict__ out) {
+  constexpr int G = 32 / LPV, C = 8 * LPV, KMAX = 27, R = 9;
+  const int lane = threadIdx.x & 31, sub = lane % LPV, c0 = sub * 8;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p0 = warp0 * G; p0 < n; p0 += nwarp * G) {
+    const int64_t p = p0 + lane / LPV;
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = bias ? bias[c0 + u] : 0.f;
+#pragma unroll 1
+    for (int t0 = 0; t0 < KMAX; t0 += R) {  // R positions, then R row loads in flight per lane
+      int32_t pos[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) pos[q] = (t0 + q < k3 && p < n) ? ypos[(size_t)(t0 + q) * n + p] : -1;
+      uint4 v[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        v[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (pos[q] >= 0) v[q] = *reinterpret_cast<const uint4*>(prod + (size_t)pos[q] * C + c0);
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        if (pos[q] < 0) continue;  // (adding the zero vector would turn a -0 sum into +0)
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[q]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __bfloat1622float2(h[u]);
+          acc[2 * u] += f.x;
+          acc[2 * u + 1] += f.y;
+        }
+      }
+    }
+    if (p < n) {
+      if constexpr (sizeof(TO) == 2) {
+        uint4 o;
+        o.x = tc::pack_bf16(acc[0], acc[1]);
+        o.y = tc::pack_bf16(acc[2], acc[3]);
+        o.z = tc::pack_bf16(acc[4], acc[5]);
+        o.w = tc::pack_bf16(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(out + (size_t)p * C + c0) = o;
+      } else {
+        float4* o = reinterpret_cast<float4*>(out + (size_t)p * C + c0);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+  }
+}
+
 // The gather-sum fused with what follows the xCPE conv in a Block (point_transformer_v3m1_base.py:318-326 with the conv's
 // Linear folded into the taps): z = bias + sum_t prod[ypos[t][p], :] stays in registers (fp32, never rounded to bf16),
 // y = res + LN0(z) is written as the new fp32 residual stream and LN1(y) as the bf16 operand of the qkv GEMM.  One warp
@@ -275,6 +332,25 @@ int ss_subm_conv_reduce(const void* prod_bf16, const int32_t* ypos, const float*
   if (n == 0) return SS_OK;
   if (!prod_bf16 || !ypos || !out) return SS_BAD_ARGS;
   if (cout > 1024) return SS_BAD_ARGS;
+  if (k3 <= 27 && (cout == 32 || cout == 64 || cout == 128)) {  // several voxels per warp
+    const int lpv = cout / 8;
+    const int nblocks = (int)ss::imin64(ss::ceil_div64(n, 8 * (32 / lpv)), 32 * ss::kNumSMs);
+#define SS_REDN_(TO, LPV)                                                                                              \
+  ss::conv_reduce_narrow_kernel<TO, LPV><<<nblocks, 256, 0, stream>>>((const __nv_bfloat16*)prod_bf16, ypos, bias, n, k3, \
+                                                                      (TO*)out)
+#define SS_REDN_L_(TO)                     \
+  do {                                     \
+    if (lpv == 4) SS_REDN_(TO, 4);         \
+    else if (lpv == 8) SS_REDN_(TO, 8);    \
+    else SS_REDN_(TO, 16);                 \
+  } while (0)
+    if (out_is_bf16) SS_REDN_L_(__nv_bfloat16);
+    else SS_REDN_L_(float);
+#undef SS_REDN_L_
+#undef SS_REDN_
+    SS_CHECK_LAUNCH();
+    return SS_OK;
+  }
   const int blocks = (int)ss::imin64(ss::ceil_div64(n, 8), 32 * ss::kNumSMs);
   const int j = (cout + 255) / 256;
 #define SS_RED_(TO, J) \
