@@ -239,9 +239,10 @@ int ss_add_layernorm(const float* res, const void* delta, int delta_is_bf16, con
 
 /* out = F.normalize(res + delta, p=2, dim=1, eps) (fp32) in one pass: the last Block's residual add
  * (point_transformer_v3m1_base.py:334-336) fused with the L2 normalisation LangPretrainer applies to the backbone output
- * (models/default.py:98).  channels % 8 == 0, <= 1024; 16-byte aligned pointers. */
+ * (models/default.py:98).  out_bf16 (nullable) receives the same rows rounded to bf16 (the operand of ss_lang_head_tc).
+ * channels % 8 == 0, <= 1024; 16-byte aligned pointers. */
 int ss_add_l2_normalize(const float* res, const void* delta, int delta_is_bf16, float eps, int64_t n, int channels,
-                        float* out, void* stream);
+                        float* out, void* out_bf16, void* stream);
 
 /* out = act(x * scale[c] + shift[c]) (scale/shift nullable).  act: 0 none, 1 GELU(erf). */
 int ss_affine_act(const void* x, int in_is_bf16, const float* scale, const float* shift, int act, int64_t n,

@@ -53,7 +53,7 @@ SIGNATURES = {
     "ss_patch_attention_backward_workspace_bytes": (_sz, [_i64, _i, _i]),
     "ss_patch_attention_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i64, _vp, _vp, _sz, _vp]),
     "ss_add_layernorm": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _i64, _i, _vp, _vp, _i, _vp]),
-    "ss_add_l2_normalize": (_i, [_vp, _vp, _i, _f, _i64, _i, _vp, _vp]),
+    "ss_add_l2_normalize": (_i, [_vp, _vp, _i, _f, _i64, _i, _vp, _vp, _vp]),
     "ss_affine_act": (_i, [_vp, _i, _vp, _vp, _i, _i64, _i, _vp, _i, _vp]),
     "ss_l2_normalize": (_i, [_vp, _i, _i64, _i, _f, _vp, _i, _vp]),
     "ss_lang_head": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -138,7 +138,8 @@ template <typename TD, typename TN, int TPR, int NCH>
 __global__ void __launch_bounds__(256)
 add_layernorm_vec_kernel(const float* res, const TD* __restrict__ delta, const float* __restrict__ g0,
                          const float* __restrict__ b0, const float* __restrict__ g1, const float* __restrict__ b1,
-                         float eps, int64_t n, int C, float* res_out, TN* __restrict__ norm_out, float l2_eps = 0.f) {
+                         float eps, int64_t n, int C, float* res_out, TN* __restrict__ norm_out, float l2_eps = 0.f,
+                         __nv_bfloat16* __restrict__ shadow_out = nullptr) {
   constexpr int RPW = 32 / TPR;  // rows per warp
   const int lane = threadIdx.x & 31, t = lane % TPR, sub = lane / TPR;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -239,6 +240,7 @@ add_layernorm_vec_kernel(const float* res, const TD* __restrict__ delta, const f
             for (int e = 0; e < 8; ++e) o[e] = v[u][e] * rstd;  // (rstd = 1 unless L2-normalising)
           }
           st8(norm_out + (size_t)r * C + c * 8, o);
+          if (shadow_out) st8(shadow_out + (size_t)r * C + c * 8, o);  // bf16 copy of the same row (operand of the head GEMM)
         }
       }
     }
@@ -372,15 +374,16 @@ int ss_add_layernorm(const float* res, const void* delta, int delta_is_bf16, con
 }
 
 // out = F.normalize(res + delta, p=2, dim=1, eps) in one pass: the last Block's residual add fused with the L2 normalisation
-// LangPretrainer applies to the backbone output (models/default.py:98); neither the un-normalised sum nor a bf16 copy is
-// written.  channels % 8 == 0, <= 1024, 16-byte aligned pointers.
+// LangPretrainer applies to the backbone output (models/default.py:98); the un-normalised sum is not written.  out_bf16
+// (nullable) receives the same rows rounded to bf16: the operand of the zero-shot head's GEMM (saves the separate
+// fp32 -> bf16 pass over [n, channels]).  channels % 8 == 0, <= 1024, 16-byte aligned pointers.
 int ss_add_l2_normalize(const float* res, const void* delta, int delta_is_bf16, float eps, int64_t n, int channels,
-                        float* out, void* stream_) {
+                        float* out, void* out_bf16, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n < 0 || channels < 8 || channels % 8 != 0 || channels > 1024 || !(eps > 0.f)) return SS_BAD_ARGS;
   if (n == 0) return SS_OK;
   if (!res || !delta || !out) return SS_BAD_ARGS;
-  if ((((uintptr_t)res | (uintptr_t)delta | (uintptr_t)out) % 16) != 0) return SS_BAD_ARGS;
+  if ((((uintptr_t)res | (uintptr_t)delta | (uintptr_t)out | (uintptr_t)out_bf16) % 16) != 0) return SS_BAD_ARGS;
   const int nchunk = channels / 8;
   int tpr = 1;
   while (tpr < 32 && tpr < nchunk) tpr <<= 1;
@@ -390,7 +393,7 @@ int ss_add_l2_normalize(const float* res, const void* delta, int delta_is_bf16, 
 #define SS_L2_(TD, T, N)                                                                                            \
   ss::add_layernorm_vec_kernel<TD, float, T, N><<<vblocks, 256, 0, stream>>>(res, (const TD*)delta, nullptr, nullptr,   \
                                                                              nullptr, nullptr, 0.f, n, channels, nullptr, \
-                                                                             out, eps)
+                                                                             out, eps, (__nv_bfloat16*)out_bf16)
 #define SS_L2_T_(TD)                       \
   do {                                     \
     if (tpr == 1) SS_L2_(TD, 1, 1);        \

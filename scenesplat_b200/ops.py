@@ -5,6 +5,8 @@ computation itself (the CUDA library is the only implementation).
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -443,13 +445,31 @@ def add_layernorm(res, delta, ln0=None, ln1=None, eps=1e-5, want_res=True, norm_
     return res_out, norm_out
 
 
-def add_l2_normalize(res_f32, delta, eps=1e-12):
+_BF16_SHADOW = {}  # id(fp32 feature tensor) -> (weak reference to it, its _version, bf16 copy written by the same kernel)
+
+
+def _set_bf16_shadow(t, shadow):
+    key = id(t)  # (tensors compare elementwise: they cannot be WeakKeyDictionary keys)
+    _BF16_SHADOW[key] = (weakref.ref(t, lambda _r, k=key: _BF16_SHADOW.pop(k, None)), t._version, shadow)
+
+
+def bf16_shadow(t):
+    """The bf16 copy a fused kernel wrote beside the fp32 tensor `t`, if `t` has not been modified in place since."""
+    ent = _BF16_SHADOW.get(id(t))
+    return ent[2] if ent is not None and ent[0]() is t and ent[1] == t._version else None
+
+
+def add_l2_normalize(res_f32, delta, eps=1e-12, want_bf16=True):
     """F.normalize(res + delta, p=2, dim=1, eps) in one pass (fp32 out): the backbone's last residual add fused with
-    LangPretrainer's normalisation."""
+    LangPretrainer's normalisation.  With want_bf16 the kernel also writes the rows rounded to bf16 (what the zero-shot
+    head's GEMM reads: lang_head_argmax / lang_head_accumulate pick it up through bf16_shadow, no conversion pass)."""
     n, c = res_f32.shape
     out = torch.empty((n, c), dtype=torch.float32, device=res_f32.device)
-    L.call("ss_add_l2_normalize", L.ptr(res_f32), L.ptr(delta), _isbf(delta), float(eps), n, c, L.ptr(out), L.stream(),
-           meta=dict(bytes=float(n * c * (8 + delta.element_size()))))
+    shadow = torch.empty((n, c), dtype=_BF16, device=res_f32.device) if want_bf16 else None
+    L.call("ss_add_l2_normalize", L.ptr(res_f32), L.ptr(delta), _isbf(delta), float(eps), n, c, L.ptr(out), L.ptr(shadow),
+           L.stream(), meta=dict(bytes=float(n * c * (8 + delta.element_size() + (2 if want_bf16 else 0)))))
+    if want_bf16:
+        _set_bf16_shadow(out, shadow)
     return out
 
 
@@ -537,7 +557,10 @@ def _head_tc_ok(feat, text):
 def _head_operand(feat, normalize):
     if normalize:
         return l2_normalize(feat, out_dtype=_BF16)
-    return feat if feat.dtype == _BF16 else feat.to(_BF16)
+    if feat.dtype == _BF16:
+        return feat
+    sh = bf16_shadow(feat)
+    return sh if sh is not None else feat.to(_BF16)
 
 
 def lang_head_argmax(feat, text, normalize=False, threshold=0.1, impl="auto"):

@@ -378,5 +378,13 @@ def test_add_l2_normalize(n, c, bf):
     want = F.normalize(res + delta.float(), p=2, dim=1, eps=1e-12)
     got = ops.add_l2_normalize(res, delta, eps=1e-12)
     np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=2e-6, atol=1e-7)
+    # the bf16 copy written by the same kernel is the rounding torch would produce, is what the head's GEMM operand
+    # lookup returns, and is dropped once the fp32 tensor is modified in place
+    sh = ops.bf16_shadow(got)
+    assert sh is not None and sh.dtype == torch.bfloat16 and torch.equal(sh, got.bfloat16())
+    assert ops._head_operand(got, False) is sh
+    assert ops.bf16_shadow(ops.add_l2_normalize(res, delta, eps=1e-12, want_bf16=False)) is None
+    got.mul_(2.0)
+    assert ops.bf16_shadow(got) is None
     zero = ops.add_l2_normalize(torch.zeros(4, c).cuda(), torch.zeros(4, c).cuda().bfloat16(), eps=1e-12)
     assert float(zero.abs().max()) == 0.0  # eps guards the zero row, as in F.normalize
