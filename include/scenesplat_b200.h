@@ -117,6 +117,12 @@ int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* bat
                   const int64_t* order_row, int64_t n, int depth, int order_id, int k, int32_t* nbr,
                   int64_t* tap_count_dev, void* workspace, size_t workspace_bytes, void* stream);
 
+/* nbr_to [k_to^3, n] / count_to [k_to^3] = the rows of the k_from^3 map of the SAME voxel set that belong to the centred
+ * k_to^3 window (k_from - k_to even and positive): the level-0 3^3 map of the xCPE convs from the stem's 5^3 map, without a
+ * second search.  Identical to ss_kmap_build(..., k_to). */
+int ss_kmap_subset(const int32_t* nbr_from, const int64_t* count_from, int64_t n, int k_from, int k_to, int32_t* nbr_to,
+                   int64_t* count_to, void* stream);
+
 /* Compacted pair lists for the gather-GEMM path: tap t owns rows [tap_base[t], tap_base[t] + count[t])
  * of the product buffer; pair_in [p_pad] = input row of every product row, ypos [k^3, n] = product row
  * of (tap, output voxel) or -1; ypos_rank (nullable, k = 3) [n, 32] = the same positions indexed by the output's RANK

@@ -32,6 +32,7 @@ SIGNATURES = {
     "ss_unpool_gather_add": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "ss_kmap_workspace_bytes": (_sz, [_i64, _i]),
     "ss_kmap_build": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "ss_kmap_subset": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "ss_kmap_pairs": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ss_subm_conv_simt": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _i, _vp]),
     "ss_subm_conv_gemm256": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),

@@ -248,6 +248,21 @@ pair27_kernel(const int32_t* __restrict__ nbr, const int64_t* __restrict__ order
   }
 }
 
+// The k_to^3 kernel map of a voxel set is a subset of the rows of its k_from^3 map (same voxels, k_to < k_from): tap
+// (i, j, l) of the small window is tap (i + d, j + d, l + d) of the large one, d = (k_from - k_to) / 2.  Row copy instead of a
+// second search (the level-0 3^3 map of the xCPE convs from the stem's 5^3 map).
+__global__ void __launch_bounds__(256)
+kmap_subset_kernel(const int32_t* __restrict__ from, const int64_t* __restrict__ count_from, int64_t n, int k_from, int k_to,
+                   int32_t* __restrict__ to, int64_t* __restrict__ count_to) {
+  const int t = blockIdx.y, d = (k_from - k_to) / 2;
+  const int i = t / (k_to * k_to), j = (t / k_to) % k_to, l = t % k_to;
+  const int tf = ((i + d) * k_from + (j + d)) * k_from + (l + d);
+  const int32_t* src = from + (size_t)tf * n;
+  int32_t* dst = to + (size_t)t * n;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) dst[p] = src[p];
+  if (blockIdx.x == 0 && threadIdx.x == 0) count_to[t] = count_from[tf];
+}
+
 // Order of the product tiles for the fused conv: position of tile t = number of tiles with a smaller (first rank, index)
 // key.  T is a few thousand (7.6 k at the benchmark chunk): T^2 comparisons from shared-memory chunks, no sort.  Eight
 // lanes share one tile (each takes every eighth candidate; a warp reads eight distinct words per step, broadcast to its
@@ -324,6 +339,19 @@ int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* bat
                                                                     (unsigned long long*)tap_count_dev);
   SS_CHECK_LAUNCH();
   ss::kmap_center_count<<<1, 32, 0, stream>>>((unsigned long long*)tap_count_dev, k3 / 2, n);
+  SS_CHECK_LAUNCH();
+  return SS_OK;
+}
+
+int ss_kmap_subset(const int32_t* nbr_from, const int64_t* count_from, int64_t n, int k_from, int k_to, int32_t* nbr_to,
+                   int64_t* count_to, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || k_to < 1 || k_from <= k_to || (k_from - k_to) % 2 != 0 || k_from > 9 || !count_from || !count_to)
+    return SS_BAD_ARGS;
+  if (n > 0 && (!nbr_from || !nbr_to)) return SS_BAD_ARGS;
+  const int blocks = n > 0 ? (int)ss::imin64(ss::ceil_div64(n, 256), 2 * ss::kNumSMs) : 1;
+  ss::kmap_subset_kernel<<<dim3(blocks, k_to * k_to * k_to), 256, 0, stream>>>(nbr_from, count_from, n, k_from, k_to, nbr_to,
+                                                                            count_to);
   SS_CHECK_LAUNCH();
   return SS_OK;
 }

@@ -205,6 +205,15 @@ def kmap_build(grid_coord, batch, code_row, order_row, depth: int, order_id: int
     return nbr, cnt
 
 
+def kmap_subset(nbr_from, count_from, k_from: int, k_to: int):
+    """(nbr, tap_count) of the centred k_to^3 window out of a k_from^3 kernel map of the same voxels (row copies)."""
+    n, dev = nbr_from.shape[1], nbr_from.device
+    nbr = torch.empty((k_to ** 3, n), dtype=torch.int32, device=dev)
+    cnt = torch.empty(k_to ** 3, dtype=torch.int64, device=dev)
+    L.call("ss_kmap_subset", L.ptr(nbr_from), L.ptr(count_from), n, k_from, k_to, L.ptr(nbr), L.ptr(cnt), L.stream())
+    return nbr, cnt
+
+
 def upload(values, dtype, device):
     """Small host table -> device WITHOUT draining the stream: torch.tensor(..., device=cuda) copies from pageable
     memory and synchronises; a pinned staging buffer with non_blocking=True only enqueues the copy (the pinned block

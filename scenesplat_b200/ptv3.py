@@ -597,6 +597,11 @@ class PointTransformerV3(PointModule):
         from .spconv_compat import kernel_map_for
         if not any(isinstance(m, Block) and m.cpe[0].tensor_core_ok() for m in self.modules()):
             return
+        stem = self.embedding.stem._modules.get("conv")
+        if getattr(stem, "kernel_size", 3) == 5 and not stem.tensor_core_ok():
+            # the stem's 5^3 map first (here, in the index phase, instead of lazily in front of the stem conv): the level's
+            # 3^3 map is then a row subset of it (ss_kmap_subset) and needs no search of its own
+            kernel_map_for(point, 5, want_pairs=False)
         kernel_map_for(point, 3, want_pairs=True)
         level = point
         holder = point  # Dict that receives the plan of the next pooling

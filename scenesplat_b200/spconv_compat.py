@@ -86,13 +86,22 @@ def kernel_map_for(point, k: int, want_pairs: bool):
     if ent is None:
         names = point.serialized_order_names
         row = next((i for i, nm in enumerate(names) if nm in ("z", "z-trans")), 0)
-        nbr, cnt = ops.kmap_build(point.grid_coord, point.batch, point.serialized_code[row], point.serialized_order[row],
-                                  point.serialized_depth, ops.ORDER_IDS[names[row]], k)
+        k_big = next((kk for kk in sorted(cache) if kk > k and (kk - k) % 2 == 0 and cache[kk]["row"] == row), None)
+        if k_big is not None:  # a larger map of the same voxels exists (the stem's 5^3): its rows contain this window
+            nbr, cnt = ops.kmap_subset(cache[k_big]["nbr"], cache[k_big]["count"], k_big, k)
+        else:
+            nbr, cnt = _kmap_search(point, row, k)
         ent = dict(nbr=nbr, count=cnt, row=row, pairs=None)
         cache[k] = ent
     if want_pairs and ent["pairs"] is None:
         ent["pairs"] = ops.kmap_pairs(ent["nbr"], point.serialized_order[ent["row"]], k, ent["count"].cpu().numpy())
     return ent
+
+
+def _kmap_search(point, row, k):
+    names = point.serialized_order_names
+    return ops.kmap_build(point.grid_coord, point.batch, point.serialized_code[row], point.serialized_order[row],
+                          point.serialized_depth, ops.ORDER_IDS[names[row]], k)
 
 
 class SubMConv3d(nn.Module):

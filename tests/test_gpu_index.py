@@ -217,6 +217,33 @@ def test_kernel_map_vs_oracle(k, row):
     assert pairs["p_pad"] % 128 == 0
 
 
+def test_kernel_map_subset_equals_search():
+    """The 3^3 map taken as a row subset of the 5^3 map (ss_kmap_subset: what PointTransformerV3.plan_indices does at level 0
+    behind the stem's map) is the map a search of its own produces, counts included; a duplicated voxel resolves to the
+    smallest index as the lower-bound search of rounds 1 - 2 did."""
+    from scenesplat_b200 import ops
+    _, g, offset = _parent(15000, seed=9)
+    batch = oser.offset2batch(offset)
+    code, order, inv, depth = oser.serialization(g, batch, len(offset), ORDERS)
+    args = (dev(g), dev(batch), dev(code[0]), dev(order[0]), depth, 0)
+    nbr5, cnt5 = ops.kmap_build(*args, 5)
+    nbr3, cnt3 = ops.kmap_build(*args, 3)
+    sub, csub = ops.kmap_subset(nbr5, cnt5, 5, 3)
+    assert torch.equal(sub, nbr3) and torch.equal(csub, cnt3)
+    ref = oconv.kernel_map(g, batch, 3)
+    np.testing.assert_array_equal(sub.cpu().numpy().T, ref)
+    # a duplicated voxel (legal input, not produced by GridSample): the LOOKED-UP taps (t < 13) of every other voxel
+    # resolve to the smaller index (the mirrored taps are written by both copies, as in rounds 1 - 2)
+    _, g1, off1 = _parent(6000, seed=10, nb=1)
+    g2 = np.concatenate([g1, g1[:1]], 0)
+    b2 = np.zeros(g2.shape[0], dtype=np.int64)
+    code2, order2, _, depth2 = oser.serialization(g2, b2, 1, ORDERS)
+    nbr_d, _ = ops.kmap_build(dev(g2), dev(b2), dev(code2[0]), dev(order2[0]), depth2, 0, 3)
+    nd = nbr_d.cpu().numpy()
+    assert not (nd[:13, :-1] == g2.shape[0] - 1).any()
+    np.testing.assert_array_equal(nd[:13, -1], nd[:13, 0])  # the copy sees voxel 0's neighbours
+
+
 def test_patch_table_vs_golden(golden):
     from scenesplat_b200 import ops
     g = golden("patch_table.npz")
