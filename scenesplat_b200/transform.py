@@ -19,6 +19,10 @@ from .registry import TRANSFORMS
 
 @TRANSFORMS.register_module()
 class GridSample(object):
+    """transform.py:1211-1330.  Voxel index = floor(float64(coord) / grid_size), i.e. the reference's
+    `coord / np.array(grid_size)` as NumPy >= 2 evaluates it for float32 coordinates (NumPy 1.x keeps that division in
+    float32: ids at exact cell boundaries can differ; the golden fixtures were generated with NumPy 2.3)."""
+
     def __init__(self, grid_size=0.05, hash_type="fnv", mode="train", keys=("coord", "color", "normal", "segment"),
                  return_inverse=False, return_grid_coord=False, return_min_coord=False, return_displacement=False,
                  project_displacement=False, importance_sample_key=None, apply_to_pc=True, device="cuda"):
