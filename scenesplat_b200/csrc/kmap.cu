@@ -50,14 +50,17 @@ kmap_insert_kernel(const int64_t* __restrict__ code, int64_t n, KmapSlot* __rest
 }
 
 // One thread per voxel p (coalesced coordinate reads and direct-tap writes); the lower half of the taps is looked up,
-// the mirrored tap is written at the neighbour.
-template <typename CoordT>
+// the mirrored tap is written at the neighbour.  K is a template parameter (tap offsets are constants of the unrolled
+// loop: no integer divisions), and for the z orders the key of a neighbour is the OR of three per-axis terms that are
+// spread ONCE per voxel and offset (3 K spreads instead of 3 per tap: ncu put the first version of this kernel at 245
+// warp instructions per lookup, issue-bound, most of them the 64-bit bit interleave).
+template <typename CoordT, int K, bool ZORDER>
 __global__ void __launch_bounds__(256)
 kmap_search_kernel(const CoordT* __restrict__ grid_coord, const int64_t* __restrict__ batch,
                    const KmapSlot* __restrict__ table, int shift, uint32_t mask, int64_t n, int depth,
-                   int order_id, int k, int32_t* __restrict__ nbr, unsigned long long* __restrict__ tap_count) {
-  extern __shared__ unsigned int s_cnt[];  // [k^3 / 2]
-  const int k3 = k * k * k, half = k3 / 2, r = k / 2;
+                   int order_id, int32_t* __restrict__ nbr, unsigned long long* __restrict__ tap_count) {
+  constexpr int k3 = K * K * K, half = k3 / 2, r = K / 2;
+  __shared__ unsigned int s_cnt[half];
   for (int i = threadIdx.x; i < half; i += blockDim.x) s_cnt[i] = 0u;
   __syncthreads();
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,14 +75,34 @@ kmap_search_kernel(const CoordT* __restrict__ grid_coord, const int64_t* __restr
     nbr[(size_t)half * n + p] = (int32_t)p;  // centre tap
   }
   const int lim = 1 << depth;
+  // per-axis key terms of the K offsets (z orders): bit i of the first curve axis -> 3 i + 2, second -> 3 i + 1, z -> 3 i;
+  // z-trans swaps the roles of x and y.  ~0ull marks an offset outside the grid.
+  uint64_t kx[K], ky[K], kz[K];
+#pragma unroll
+  for (int d = 0; ZORDER && d < K; ++d) {
+    const int qx = x + d - r, qy = y + d - r, qz = z + d - r;
+    kx[d] = (qx >= 0 && qx < lim) ? spread3((uint64_t)qx) << (order_id == 1 ? 1 : 2) : ~0ull;
+    ky[d] = (qy >= 0 && qy < lim) ? spread3((uint64_t)qy) << (order_id == 1 ? 2 : 1) : ~0ull;
+    kz[d] = (qz >= 0 && qz < lim) ? spread3((uint64_t)qz) : ~0ull;
+  }
   const uint4* slots = reinterpret_cast<const uint4*>(table);
+#pragma unroll(ZORDER ? half : 1)  // (the Hilbert variant keeps a rolled loop: its key is ~200 instructions per tap)
   for (int t = 0; t < half; ++t) {
-    const int dx = t / (k * k) - r, dy = (t / k) % k - r, dz = t % k - r;
+    constexpr int KK = K * K;
+    const int i = t / KK, j = (t / K) % K, l = t % K;  // constants after unrolling
     int32_t found = -1;
     if (active) {
-      const int qx = x + dx, qy = y + dy, qz = z + dz;
-      if (qx >= 0 && qy >= 0 && qz >= 0 && qx < lim && qy < lim && qz < lim) {
-        const uint64_t key = bpart | sfc_key(order_id, (uint32_t)qx, (uint32_t)qy, (uint32_t)qz, depth);
+      uint64_t key;
+      bool inside;
+      if (ZORDER) {
+        inside = (kx[i] != ~0ull) && (ky[j] != ~0ull) && (kz[l] != ~0ull);
+        key = bpart | kx[i] | ky[j] | kz[l];
+      } else {
+        const int qx = x + i - r, qy = y + j - r, qz = z + l - r;
+        inside = qx >= 0 && qy >= 0 && qz >= 0 && qx < lim && qy < lim && qz < lim;
+        key = inside ? (bpart | sfc_key(order_id, (uint32_t)qx, (uint32_t)qy, (uint32_t)qz, depth)) : 0ull;
+      }
+      if (inside) {
         uint32_t slot = kmap_hash(key, shift);
         while (true) {
           const uint4 e = __ldg(slots + slot);
@@ -329,14 +352,23 @@ int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* bat
   SS_CHECK_LAUNCH();
   // mirrored half (taps > centre) is only written where a neighbour exists
   SS_CUDA(cudaMemsetAsync(nbr + (size_t)(k3 / 2 + 1) * n, 0xff, (size_t)(k3 / 2) * n * 4, stream));
-  const size_t smem = (size_t)(k3 / 2) * 4;
-  if (coord_is_int32)
-    ss::kmap_search_kernel<int><<<blocks, 256, smem, stream>>>((const int*)grid_coord, batch, table, shift, mask, n, depth,
-                                                              order_id, k, nbr, (unsigned long long*)tap_count_dev);
-  else
-    ss::kmap_search_kernel<long long><<<blocks, 256, smem, stream>>>((const long long*)grid_coord, batch, table, shift,
-                                                                    mask, n, depth, order_id, k, nbr,
-                                                                    (unsigned long long*)tap_count_dev);
+#define SS_KSEARCH_(T, KK, Z)                                                                                           \
+  ss::kmap_search_kernel<T, KK, Z><<<blocks, 256, 0, stream>>>((const T*)grid_coord, batch, table, shift, mask, n, depth,  \
+                                                               order_id, nbr, (unsigned long long*)tap_count_dev)
+#define SS_KSEARCH_K_(T, Z)        \
+  do {                             \
+    if (k == 3) SS_KSEARCH_(T, 3, Z); \
+    else SS_KSEARCH_(T, 5, Z);     \
+  } while (0)
+  if (order_id < 2) {
+    if (coord_is_int32) SS_KSEARCH_K_(int, true);
+    else SS_KSEARCH_K_(long long, true);
+  } else {
+    if (coord_is_int32) SS_KSEARCH_K_(int, false);
+    else SS_KSEARCH_K_(long long, false);
+  }
+#undef SS_KSEARCH_K_
+#undef SS_KSEARCH_
   SS_CHECK_LAUNCH();
   ss::kmap_center_count<<<1, 32, 0, stream>>>((unsigned long long*)tap_count_dev, k3 / 2, n);
   SS_CHECK_LAUNCH();
