@@ -91,6 +91,33 @@ def linear_params(lin: nn.Linear):
                                lin.bias.detach().float().clone() if lin.bias is not None else None))
 
 
+def linear_bn_params(lin: nn.Linear, bn):
+    """Linear followed by an eval-mode BatchNorm1d as ONE Linear: (bf16 weight * scale[:, None], fp32 bias * scale + shift),
+    composed in fp32 and cached on the Linear (both modules' parameters and running statistics are the cache key)."""
+    if bn is None:
+        return linear_params(lin)
+
+    def fn():
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+        shift = bn.bias.detach().float() - bn.running_mean.float() * scale
+        w = (lin.weight.detach().float() * scale[:, None]).to(BF16).contiguous()
+        b = shift if lin.bias is None else lin.bias.detach().float() * scale + shift
+        return w, b.contiguous()
+    deps = [lin.weight] + ([lin.bias] if lin.bias is not None else []) + [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+    return _cache.get(lin, "lin_bn", deps, fn)
+
+
+def linear_bn_act_bf16(lin: nn.Linear, bn, x, act=0):
+    """act(BatchNorm1d_eval(Linear(x))) in the GEMM's epilogue (BN folded into the weights, exact GELU when act = 1)."""
+    w, b = linear_bn_params(lin, bn)
+    if x.dtype != BF16:
+        x = x.to(BF16)
+    if x.is_cuda and ops.linear_ok(lin.in_features, lin.out_features):
+        return ops.linear_act(x, w, b, act=act)
+    y = F.linear(x, w, b.to(BF16))
+    return ops.affine_act(y, act=1) if act else y
+
+
 def linear_bf16(lin: nn.Linear, x, act=0):
     """nn.Linear (+ exact GELU when act = 1) on bf16 operands with fp32 accumulation: the package's tcgen05 CTA-pair GEMM
     (csrc/gemm2cta.cu) with bias / activation in the epilogue.  Channel counts outside its tiling (K not a multiple of
@@ -457,14 +484,15 @@ class SerializedUnpooling(PointModule):
         lin_s, bn_s, act_s, ok_s = self._branch(self.proj_skip)
         if not (ok_p and ok_s and (act_p is None) == (act_s is None)):
             raise NotImplementedError("SerializedUnpooling: only Linear[+BatchNorm1d][+GELU] branches are built")
-        a = linear_bf16(lin_p, _bf16_of(point, point.feat))
-        s = linear_bf16(lin_s, _bf16_of(parent, parent.feat))
-        sc_s, sh_s = bn_fold(bn_s) if bn_s is not None else (None, None)
-        sc_p, sh_p = bn_fold(bn_p) if bn_p is not None else (None, None)
-        # `skip` is only ever read as the bf16 operand of the next block's xCPE conv: written as bf16 directly
-        # (fp32 in the reference; saves the fp32 write and a separate cast pass over N x C)
-        out, skip = ops.unpool_gather_add(s, a, inverse, sc_s, sh_s, sc_p, sh_p, 1 if act_s is not None else 0,
-                                          out_dtype=torch.float32, want_a=True, a_dtype=BF16)
+        # Both branches are Linear -> BatchNorm1d(eval) -> GELU (ref :447-470): BN is folded into the Linear and the GELU runs
+        # in the GEMM's epilogue on the fp32 accumulators, so the coarse branch is activated once per COARSE row (not once
+        # per fine voxel that gathers it) and the pass below is a plain gather-add.  (ncu put the previous form, which
+        # evaluated both activations inside the gather pass, at 52 % XU / 69 % issue: bound by the two GELUs per element.)
+        act = 1 if act_s is not None else 0
+        a = linear_bn_act_bf16(lin_p, bn_p, _bf16_of(point, point.feat), act)
+        # `skip` is only ever read as the bf16 operand of the next block's xCPE conv: the GEMM's bf16 output is it
+        skip = linear_bn_act_bf16(lin_s, bn_s, _bf16_of(parent, parent.feat), act)
+        out, _ = ops.unpool_gather_add(skip, a, inverse, None, None, None, None, 0, out_dtype=torch.float32, want_a=False)
         parent.feat = out
         # ref :478 rebinds parent.feat only: sparse_conv_feat keeps the skip projection (oracle/ptv3.py)
         parent.sparse_conv_feat = parent.sparse_conv_feat.replace_feature(skip)
