@@ -170,15 +170,17 @@ struct PairRuns {
 // 128-byte status line and reads the lines of all earlier tiles in parallel (warp = tile, lane = tap): no chained look-back.
 // ypos_rank rows leave through a per-warp shared-memory transposition as full 128-byte lines (columns 27..31 = -1).
 constexpr int kPairThreads = 256;
-constexpr int kPairItems = 4;
-constexpr int kPairTile = kPairThreads * kPairItems;
-inline size_t pair27_workspace_bytes(int64_t n) { return 256 + (size_t)ceil_div64(n > 0 ? n : 1, kPairTile) * 128; }
+// ranks per thread: 4 at the benchmark chunk's level 0 (293 CTAs = one wave at two CTAs per SM), fewer at the coarser levels,
+// where a level is a few dozen CTAs and the per-thread serial work (27 taps x items) sets the time (ncu: 39 us for 9 CTAs)
+inline int pair27_items(int64_t n) { return n > 150000 ? 4 : (n > 40000 ? 2 : 1); }
+inline size_t pair27_workspace_bytes(int64_t n) { return 256 + (size_t)ceil_div64(n > 0 ? n : 1, kPairThreads) * 128; }
 
+template <int kPairItems>
 __global__ void __launch_bounds__(kPairThreads, 2)
 pair27_kernel(const int32_t* __restrict__ nbr, const int64_t* __restrict__ order, const int64_t* __restrict__ tap_base,
               int64_t n, uint32_t* counter, uint32_t* status, int32_t* __restrict__ pair_in, int32_t* __restrict__ ypos,
               int32_t* __restrict__ ypos_rank, int32_t* __restrict__ tile_first_rank) {
-  constexpr int K3 = 27, W = kPairThreads / 32;
+  constexpr int K3 = 27, W = kPairThreads / 32, kPairTile = kPairThreads * kPairItems;
   __shared__ uint32_t s_cnt[kPairItems * W][K3];  // ballot totals per (item, warp), then their exclusive scan per tap
   __shared__ uint32_t s_part[W][32];
   __shared__ uint32_t s_before[32];
@@ -405,10 +407,16 @@ int ss_kmap_pairs(const int32_t* nbr, const int64_t* order_row, int64_t n, int k
   int rc = SS_OK;
   if (k == 3) {
     SS_CUDA(cudaMemsetAsync(ws, 0, ss::pair27_workspace_bytes(n), stream));
-    const int ptiles = (int)ss::ceil_div64(n, ss::kPairTile);
-    ss::pair27_kernel<<<ptiles, ss::kPairThreads, 0, stream>>>(nbr, order_row, tap_base_dev, n, (uint32_t*)ws,
-                                                              (uint32_t*)(ws + 256), pair_in, ypos, ypos_rank,
-                                                              tile_first_rank);
+    const int items = ss::pair27_items(n);
+    const int ptiles = (int)ss::ceil_div64(n, (int64_t)ss::kPairThreads * items);
+#define SS_PAIR27_(I)                                                                                                  \
+  ss::pair27_kernel<I><<<ptiles, ss::kPairThreads, 0, stream>>>(nbr, order_row, tap_base_dev, n, (uint32_t*)ws,          \
+                                                               (uint32_t*)(ws + 256), pair_in, ypos, ypos_rank,         \
+                                                               tile_first_rank)
+    if (items == 4) SS_PAIR27_(4);
+    else if (items == 2) SS_PAIR27_(2);
+    else SS_PAIR27_(1);
+#undef SS_PAIR27_
     SS_CHECK_LAUNCH();
   } else {
     ss::PairRuns f{nbr, order_row, tap_base_dev, n, pair_in, ypos, ypos_rank, tile_first_rank};
