@@ -455,9 +455,13 @@ def main():
             roofline["binding_pipe"] = dict(pipe="MUFU.EX2", achieved=exp_rate / 1e12, peak=MUFU_PEAK_TEXP, unit="Texp/s",
                                             frac=exp_rate / 1e12 / MUFU_PEAK_TEXP,
                                             peak_source="measured, tools/micro/mufu.cu (16 / clk / SM at 1.955 GHz)")
+        # (the narrow convs -- C = 32 / 64 / 128, K too small for the tensor pipe -- are bound by the gathered rows and the
+        # products they write: their fraction of the HBM rate on the algorithmic bytes stands beside the tensor fraction)
         roofline["other_hot_kernels"] = {
             k: dict(ms_per_step=v["ms"] / args.steps, tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12,
-                    frac=v["flops"] / (v["ms"] * 1e-3) / 1e12 / pk["tf_sust"]) for k, v in hot_table.items() if k != name}
+                    frac=v["flops"] / (v["ms"] * 1e-3) / 1e12 / pk["tf_sust"],
+                    **({"gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9, "frac_of_hbm": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"]}
+                       if v.get("bytes") else {})) for k, v in hot_table.items() if k != name}
     own_ms = sum(r["ms"] for r in own.values()) / prof_steps
     # the second half of BASELINE.json's metric: serialize + pool achieved HBM GB/s (algorithmic bytes of SURVEY 8d:
     # 128 B / Gaussian for the 4-order serialization, N (28 + C e) + M (148 + 4 C) for a pooling level)
