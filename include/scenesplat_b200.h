@@ -110,9 +110,11 @@ int ss_unpool_gather_add(const void* a, const void* b, int in_is_bf16, const int
  * point_transformer_v3m1_base.py:277-284 and :499-506). */
 size_t ss_kmap_workspace_bytes(int64_t n, int k);
 
-/* Neighbour table nbr [k^3, n] int32 (tap-major, -1 = inactive) from one sorted serialization row
- * (code_row/order_row [n], encoded with order_id at `depth`).  tap t = (i*k+j)*k+l <-> (i-r, j-r, l-r).
- * tap_count_dev [k^3] int64 receives the number of active pairs per tap. */
+/* Neighbour table nbr [k^3, n] int32 (tap-major, -1 = inactive) from one serialization row
+ * (code_row [n], encoded with order_id at `depth`; order_row [n] = its sorting permutation, part of the contract -- the
+ * pair lists walk it -- but not read by the build since it keeps the codes in a transient open-addressing table inside
+ * `workspace`: 16 B x 2^ceil(log2(2 n)) slots).  tap t = (i*k+j)*k+l <-> (i-r, j-r, l-r).  Equal codes (duplicated
+ * voxels) resolve to the smallest voxel index.  tap_count_dev [k^3] int64 receives the number of active pairs per tap. */
 int ss_kmap_build(const void* grid_coord, int coord_is_int32, const int64_t* batch, const int64_t* code_row,
                   const int64_t* order_row, int64_t n, int depth, int order_id, int k, int32_t* nbr,
                   int64_t* tap_count_dev, void* workspace, size_t workspace_bytes, void* stream);
