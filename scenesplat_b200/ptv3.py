@@ -114,7 +114,7 @@ def linear_bn_act_bf16(lin: nn.Linear, bn, x, act=0):
         x = x.to(BF16)
     if x.is_cuda and ops.linear_ok(lin.in_features, lin.out_features):
         return ops.linear_act(x, w, b, act=act)
-    y = F.linear(x, w, b.to(BF16))
+    y = F.linear(x, w, b.to(BF16) if b is not None else None)
     return ops.affine_act(y, act=1) if act else y
 
 
