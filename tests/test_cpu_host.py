@@ -44,6 +44,46 @@ def test_no_cpu_fallback():
         ops.serialize(torch.zeros((4, 3), dtype=torch.int64), torch.tensor([4]), 3, ["z"])
 
 
+def test_bf16_shadow_registry_and_weight_folds():
+    """Host logic that needs no GPU: the registry that hands the zero-shot head the bf16 rows written beside the fp32
+    features (dropped on in-place modification and when the tensor dies), and the Linear + BatchNorm1d(eval) fold of
+    SerializedUnpooling (composed in fp32, refreshed when a parameter or a running statistic changes)."""
+    import gc
+    from scenesplat_b200 import ops, ptv3
+    feat = torch.randn(5, 8)
+    sh = feat.bfloat16()
+    ops._set_bf16_shadow(feat, sh)
+    assert ops.bf16_shadow(feat) is sh and ops._head_operand(feat, False) is sh
+    assert ops.bf16_shadow(torch.randn(5, 8)) is None
+    feat.add_(1.0)
+    assert ops.bf16_shadow(feat) is None
+    other = torch.randn(3, 8)
+    ops._set_bf16_shadow(other, other.bfloat16())
+    key = id(other)
+    del other
+    gc.collect()
+    assert key not in ops._BF16_SHADOW
+
+    torch.manual_seed(0)
+    lin, bn = torch.nn.Linear(16, 32), torch.nn.BatchNorm1d(32, eps=1e-3)
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2.0)
+    bn.weight.data.normal_()
+    bn.bias.data.normal_()
+    bn.eval()
+    x = torch.randn(7, 16)
+    w, b = ptv3.linear_bn_params(lin, bn)
+    assert w.dtype == torch.bfloat16 and b.dtype == torch.float32
+    want = bn(lin(x))
+    got = x @ w.float().t() + b
+    assert float((got - want).abs().max()) < 3e-2 * float(want.abs().max())  # bf16 weights
+    assert ptv3.linear_bn_params(lin, bn)[0] is w  # cached
+    bn.running_mean.add_(1.0)
+    w2, b2 = ptv3.linear_bn_params(lin, bn)
+    assert w2 is not w and float((x @ w2.float().t() + b2 - bn(lin(x))).abs().max()) < 3e-2 * float(want.abs().max())
+    assert ptv3.linear_bn_params(lin, None)[0].shape == (32, 16)
+
+
 def test_state_dict_matches_reference_golden_keys(golden):
     import scenesplat_b200 as S
     from tests.golden.make_golden import SMALL_CFG
